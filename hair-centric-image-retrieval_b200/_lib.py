@@ -1,0 +1,89 @@
+"""ctypes binding of libhcir_b200.so (C ABI: include/hcir_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing and cannot be built,
+or the device is not a B200 (sm_100), every compute call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+HCIR_OK, HCIR_EINVAL, HCIR_EARCH, HCIR_ECUDA, HCIR_EWORKSPACE = 0, -1, -2, -3, -4
+
+
+class Plan(C.Structure):
+    """hcir_plan_t"""
+    _fields_ = [("nsplit", C.c_int32), ("cap", C.c_int32), ("kc", C.c_int32), ("reserved", C.c_int32),
+                ("counts_off", C.c_uint64), ("keys_off", C.c_uint64), ("bytes", C.c_uint64)]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_INT = C.c_int
+_F = C.c_float
+
+# name -> (restype, argtypes); every symbol include/hcir_b200.h declares
+SIGNATURES = {
+    "hcir_abi_version": (_INT, []),
+    "hcir_last_error": (C.c_char_p, []),
+    "hcir_device_supported": (_INT, []),
+    "hcir_padded_dim": (_INT, [_INT]),
+    "hcir_l2norm_cast": (_INT, [_P, _I64, _INT, _I64, _P, _P, _INT, _P, _P]),
+    "hcir_simtopk_plan": (_INT, [_I64, _I64, _INT, _INT, _INT, C.POINTER(Plan)]),
+    "hcir_simtopk": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P]),
+    "hcir_simtopk_debug": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P, _P]),
+    "hcir_select_rescore": (_INT, [_P, _P, _INT, _I64, _I64, _INT, _I64, C.POINTER(Plan), _P, _P, _F, _F,
+                                   _P, _P, _P, _P, _P]),
+    "hcir_exact_workspace_bytes": (C.c_size_t, [_I64, _I64, _INT, _INT]),
+    "hcir_exact_topk": (_INT, [_P, _P, _INT, _I64, _INT, _I64, _P, _I64, _P, _P, _P, C.c_size_t, _INT, _P]),
+    "hcir_gather_labels": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
+    "hcir_vote": (_INT, [_P, _P, _I64, _INT, _INT, _F, _P, _P, _P]),
+    "hcir_merge_topk": (_INT, [_P, _P, _P, _INT, _I64, _INT, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed and possible) the in-tree shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if build_if_missing and not _build.is_current():
+        try:
+            _build.build_library()
+        except Exception as e:  # no nvcc on this box: use the shipped .so if there is one
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    f"libhcir_b200.so is missing and could not be built ({e}); the hcir_b200 "
+                    "product path has no CPU fallback") from e
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI/header drift
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hcir_abi_version() != 1:
+        raise RuntimeError("hcir_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().hcir_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == HCIR_OK:
+        return
+    msg = f"{what}: {last_error()}" if what else last_error()
+    if rc == HCIR_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(f"[hcir rc={rc}] {msg}")

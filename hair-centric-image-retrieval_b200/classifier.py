@@ -1,0 +1,83 @@
+"""sklearn-shaped drop-in for the reference's kNN classifier call
+(HairPretraining/src/classification_engine.py:80-82):
+
+    knn = KNeighborsClassifier(n_neighbors=k, metric="cosine")
+    knn.fit(self.training_features, self.training_labels)
+    y_pred = knn.predict(self.testing_features)
+
+Swap the import for ``KNeighborsClassifierB200`` and the three lines run on the B200 kernels.
+Accepts CPU torch tensors / numpy exactly like the reference passes them; ``fit`` moves the
+bank to the GPU once."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import GalleryBank, _as_2d_f32, _to_host
+
+
+class KNeighborsClassifierB200:
+    def __init__(self, n_neighbors: int = 5, *, metric: str = "cosine", weights: str = "uniform",
+                 T: float = 0.07, device=None, mode: str = "auto"):
+        if metric != "cosine":
+            raise ValueError("KNeighborsClassifierB200 implements metric='cosine' only (the reference's "
+                             "only kNN metric, classification_engine.py:80)")
+        if weights not in ("uniform", "temperature"):
+            raise ValueError("weights must be 'uniform' (reference parity) or 'temperature' (extension)")
+        self.n_neighbors = int(n_neighbors)
+        self.metric = metric
+        self.weights = weights
+        self.T = float(T)
+        self.device = device
+        self.mode = mode
+        self._bank: GalleryBank | None = None
+
+    # sklearn API -------------------------------------------------------------------------
+    def fit(self, X, y):
+        self._bank = GalleryBank(X, y, device=self.device)
+        self.classes_ = self._bank.classes_
+        self.n_samples_fit_ = self._bank.n
+        self.n_features_in_ = self._bank.d
+        return self
+
+    def _check(self):
+        if self._bank is None:
+            raise RuntimeError("This KNeighborsClassifierB200 instance is not fitted yet")
+
+    def kneighbors(self, X=None, n_neighbors=None, return_distance=True):
+        """(dist = clip(1 - cos, 0, 2) fp32 ascending, idx int64) like sklearn's cosine brute
+        force (metrics/pairwise.py cosine_distances)."""
+        self._check()
+        if X is None:
+            raise NotImplementedError("kneighbors(X=None) (leave-one-out on the training set) is not "
+                                      "on the reference's path")
+        k = self.n_neighbors if n_neighbors is None else int(n_neighbors)
+        _, kind = _as_2d_f32(X, "X")
+        sims, idx = self._bank.topk(X, k, mode=self.mode, return_device=True)
+        if kind == "torch_cpu":
+            kind = "numpy"  # sklearn returns numpy
+        idx_h = _to_host(idx, kind)
+        if not return_distance:
+            return idx_h
+        dist = torch.clamp(1.0 - sims, 0.0, 2.0)
+        return _to_host(dist, kind), idx_h
+
+    def predict(self, X):
+        self._check()
+        T = self.T if self.weights == "temperature" else None
+        out = self._bank.predict(X, self.n_neighbors, T=T, mode=self.mode)
+        return out.numpy() if isinstance(out, torch.Tensor) and not out.is_cuda else out
+
+    def predict_multi_k(self, X, ks):
+        """All of ``Classifier.knn_eval``'s k values (classification_engine.py:71,79) from ONE
+        neighbour search at max(ks)."""
+        self._check()
+        T = self.T if self.weights == "temperature" else None
+        out = self._bank.predict_multi_k(X, ks, T=T, mode=self.mode)
+        return {k: (v.numpy() if isinstance(v, torch.Tensor) and not v.is_cuda else v) for k, v in out.items()}
+
+    def score(self, X, y):
+        pred = self.predict(X)
+        pred = pred.cpu().numpy() if isinstance(pred, torch.Tensor) else np.asarray(pred)
+        y = y.cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+        return float((pred == y).mean())

@@ -1,0 +1,231 @@
+// Shared device/host helpers for the hcir_b200 kernels (sm_100a only).
+//
+// Internal data layout (see DESIGN.md "Data layout in HBM"):
+//   * gallery / query banks are row-major with a row stride `ld` = D rounded up to 64
+//     elements, zero padded, so every row is 16-byte aligned, TMA-legal and the fp32 dot
+//     product needs no tail handling (zero padding contributes fma(0,0,acc) == acc exactly);
+//   * a top-k candidate is a single 64-bit KEY = (order-preserving bits of the fp32
+//     similarity) << 32 | (0xFFFFFFFF - gallery_index).  Larger key == better candidate:
+//     descending similarity, ties -> ascending gallery index.  This is the build's canonical
+//     order and makes every selection / merge / sort an exact
+//     operation on unique integers.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hcir_b200.h"
+
+namespace hcir {
+
+// ---- error plumbing (api.cu) -----------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int check_device();  // HCIR_OK iff current device is sm_100
+
+#define HCIR_CUDA_TRY(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::hcir::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define HCIR_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      ::hcir::set_error(__VA_ARGS__); \
+      return HCIR_EINVAL;            \
+    }                                \
+  } while (0)
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__host__ __device__ inline int64_t ceil_div_i64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up_int(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- candidate keys ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  f += 0.0f;  // canonicalise -0.0 -> +0.0 so that equal similarities have equal bits
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float sim, uint32_t idx) {
+  return (static_cast<uint64_t>(f2ord(sim)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_sim(uint64_t key) { return ord2f(static_cast<uint32_t>(key >> 32)); }
+__device__ __forceinline__ uint32_t key_idx(uint64_t key) { return 0xFFFFFFFFu - static_cast<uint32_t>(key); }
+
+// ---- canonical fp32 dot product ----------------------------------------------------------
+// One warp per (query row, gallery row).  Lane l walks float4 chunks l, l+32, ... with one
+// sequential fma chain, then a xor-butterfly adds the 32 partials.  EVERY exact similarity
+// this library returns comes from this function, so single-GPU, sharded, re-scored and
+// fallback results are bit-identical to each other regardless of which kernel produced them.
+__device__ __forceinline__ float canonical_dot(const float4* __restrict__ q4,
+                                               const float4* __restrict__ g4, int ld4, int lane) {
+  float acc = 0.0f;
+  for (int c = lane; c < ld4; c += kWarp) {
+    const float4 a = q4[c];
+    const float4 b = __ldg(g4 + c);
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    acc = fmaf(a.w, b.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  return acc;
+}
+
+// ---- warp-cooperative exact selection ("prune") -----------------------------------------
+// Keep the `keep` largest of the `cnt` (> keep) unique keys in buf[0..cnt) -- a buffer in
+// GLOBAL memory (L2 resident) -- compacted in place to buf[0..keep) in arbitrary order.
+// Returns the keep-th largest key.  MSB-first radix select, 8-bit digits; `hist` is a
+// per-warp shared-memory scratch of 256 words.  All 32 lanes must call it convergently.
+__device__ inline uint64_t warp_prune(uint64_t* buf, int cnt, int keep, uint32_t* hist, int lane) {
+  uint64_t prefix = 0, mask = 0;
+  uint32_t remaining = static_cast<uint32_t>(keep);
+  __syncwarp();
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int b = lane; b < 256; b += kWarp) hist[b] = 0;
+    __syncwarp();
+    for (int i = lane; i < cnt; i += kWarp) {
+      const uint64_t key = __ldcg(buf + i);
+      if ((key & mask) == prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & 0xFFu], 1u);
+    }
+    __syncwarp();
+    // lane l owns bins 255-8l .. 248-8l (descending), so a lane-prefix is a "count above".
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c[j] = hist[255 - (8 * lane + j)];
+      s += c[j];
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < kWarp; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - s;
+    const bool mine = (excl < remaining) && (remaining <= incl);
+    const int src = __ffs(__ballot_sync(kFull, mine)) - 1;
+    uint32_t digit = 0, newrem = 0, dcount = 0;
+    if (mine) {
+      uint32_t run = excl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (dcount == 0 && run + c[j] >= remaining) {
+          digit = 255 - (8 * lane + j);
+          newrem = remaining - run;
+          dcount = c[j];
+        }
+        run += c[j];
+      }
+    }
+    digit = __shfl_sync(kFull, digit, src);
+    remaining = __shfl_sync(kFull, newrem, src);
+    dcount = __shfl_sync(kFull, dcount, src);
+    prefix |= static_cast<uint64_t>(digit) << shift;
+    mask |= 0xFFull << shift;
+    __syncwarp();
+    if (dcount == 1 && shift > 0) {
+      // exactly one key carries this prefix: it IS the keep-th largest; fetch it and stop.
+      uint64_t found = 0;
+      for (int i = lane; i < cnt; i += kWarp) {
+        const uint64_t key = __ldcg(buf + i);
+        if ((key & mask) == prefix) found = key;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) found |= __shfl_xor_sync(kFull, found, o);
+      prefix = found;
+      break;
+    }
+  }
+  const uint64_t thr = prefix;
+  int out = 0;
+  for (int base = 0; base < cnt; base += kWarp) {
+    const int i = base + lane;
+    const uint64_t key = (i < cnt) ? __ldcg(buf + i) : 0ull;
+    const bool keepit = (i < cnt) && (key >= thr);
+    const uint32_t b = __ballot_sync(kFull, keepit);
+    __syncwarp();
+    if (keepit) buf[out + __popc(b & ((1u << lane) - 1u))] = key;
+    out += __popc(b);
+    __syncwarp();
+  }
+  return thr;
+}
+
+// ---- block-cooperative selection on a shared-memory key array ----------------------------
+// Find the `keep`-th largest of keys[0..cnt) (unique keys, 1 <= keep <= cnt) and return it to
+// every thread.  If `out` is non-null the `keep` keys >= that threshold are also written to
+// out[0..keep) (arbitrary order; `out` must not alias `keys`).  MSB-first radix select with
+// 8-bit digits.  `hist` = 256 words, `scratch` = 4 words of shared memory.  The whole block
+// must call it convergently.
+__device__ inline uint64_t block_select(const uint64_t* keys, int cnt, int keep, uint64_t* out,
+                                        uint32_t* hist, uint32_t* scratch) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  uint64_t prefix = 0, mask = 0;
+  uint32_t remaining = static_cast<uint32_t>(keep);
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int b = tid; b < 256; b += nthr) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += nthr) {
+      const uint64_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (tid < kWarp) {  // warp 0 scans the 256 bins, top bin first
+      const int lane = tid;
+      uint32_t c[8], s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j] = hist[255 - (8 * lane + j)];
+        s += c[j];
+      }
+      uint32_t incl = s;
+#pragma unroll
+      for (int o = 1; o < kWarp; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t excl = incl - s;
+      if ((excl < remaining) && (remaining <= incl)) {
+        uint32_t run = excl;
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!done && run + c[j] >= remaining) {
+            scratch[0] = 255 - (8 * lane + j);
+            scratch[1] = remaining - run;
+            done = true;
+          }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= static_cast<uint64_t>(scratch[0]) << shift;
+    mask |= 0xFFull << shift;
+    remaining = scratch[1];
+    __syncthreads();
+  }
+  const uint64_t thr = prefix;
+  if (out != nullptr) {
+    if (tid == 0) scratch[2] = 0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += nthr) {
+      const uint64_t key = keys[i];
+      if (key >= thr) out[atomicAdd(&scratch[2], 1u)] = key;
+    }
+    __syncthreads();
+  }
+  return thr;
+}
+
+}  // namespace hcir

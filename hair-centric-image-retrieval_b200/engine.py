@@ -1,0 +1,305 @@
+"""Host side of the hot path: a device-resident, L2-normalised gallery bank and the exact
+cosine top-k / kNN-vote over it.  PyTorch is plumbing only (device memory, streams); every
+arithmetic step is one of the hand-written sm_100a kernels behind the C ABI
+(include/hcir_b200.h).  There is no CPU fallback.
+
+Reference call sites this replaces (all CPU library calls in the reference):
+  * ``F.normalize`` + ``torch.cat`` feature bank   HairPretraining/src/classification_engine.py:50,62,66-69
+  * ``KNeighborsClassifier(k, metric="cosine")``  HairPretraining/src/classification_engine.py:80-82
+  * ``torch.mm(q, G.t())`` + ``torch.topk``        experiments/DualViewHair/scripts/qualitative_test.py:79-84
+  * ``cosine_similarity`` + ``np.argsort``          src/models/hair_encoder.py:193-194
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Plan
+
+_SM_COUNT_CACHE: dict[int, int] = {}
+
+
+def _sm_count(device: torch.device) -> int:
+    i = device.index if device.index is not None else torch.cuda.current_device()
+    if i not in _SM_COUNT_CACHE:
+        _SM_COUNT_CACHE[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SM_COUNT_CACHE[i]
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("hcir_b200 needs a CUDA device (B200, sm_100); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"hcir_b200 runs on CUDA devices only, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _as_2d_f32(x, name: str):
+    """Accept numpy / torch (cpu or cuda); return (torch tensor fp32 2-D, kind)."""
+    if isinstance(x, torch.Tensor):
+        kind = "torch_cuda" if x.is_cuda else "torch_cpu"
+        t = x
+    else:
+        kind = "numpy"
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32)))
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [rows, dim], got shape {tuple(t.shape)}")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t, kind
+
+
+def _to_host(t: torch.Tensor, kind: str):
+    """Device result -> the caller's flavour (numpy / cpu tensor / cuda tensor)."""
+    if kind == "torch_cuda":
+        return t
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy() if kind == "numpy" else h
+
+
+def l2_normalize(x: torch.Tensor, *, want_f32=True, want_bf16=True, want_delta=True):
+    """K1 on a device tensor [n, d] fp32 -> (unit fp32 [n, ld] | None, unit bf16 [n, ld] | None,
+    delta [n] | None) with ld = d rounded up to 64 (zero padded).  ``F.normalize(x, dim=1)``
+    semantics (classification_engine.py:50)."""
+    lib = _lib.load()
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+        raise ValueError("l2_normalize expects a 2-D fp32 CUDA tensor")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, d = x.shape
+    ld = lib.hcir_padded_dim(d)
+    dev = x.device
+    o32 = torch.empty((n, ld), dtype=torch.float32, device=dev) if want_f32 else None
+    obf = torch.empty((n, ld), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    dl = torch.empty((n,), dtype=torch.float32, device=dev) if want_delta else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.hcir_l2norm_cast(x.data_ptr(), n, d, x.stride(0),
+                                        o32.data_ptr() if want_f32 else None,
+                                        obf.data_ptr() if want_bf16 else None, ld,
+                                        dl.data_ptr() if want_delta else None, _stream_ptr()), "l2norm_cast")
+    return o32, obf, dl
+
+
+class GalleryBank:
+    """Device-resident normalised feature bank (fp32 unit rows for the exact re-score, bf16
+    unit rows for the tensor-core contraction) + optional labels.
+
+    ``features`` [N, D] may be un-normalised (hair_encoder.py embeddings) or already unit
+    (classification_engine.py bank): normalisation is idempotent up to fp32 rounding.
+    ``labels`` are arbitrary integers; they are mapped to class indices through
+    ``classes_ = unique(labels)`` exactly like sklearn's ``fit``."""
+
+    def __init__(self, features, labels=None, *, device=None, idx_offset: int = 0, classes=None,
+                 chunk_rows: int = 1 << 18):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        feats, _ = _as_2d_f32(features, "features")
+        n, d = feats.shape
+        if n < 1:
+            raise ValueError("empty gallery")
+        if n >= (1 << 31) - 256:
+            raise ValueError("a gallery shard holds fewer than 2^31 rows")
+        self.n, self.d = int(n), int(d)
+        self.ld = self.lib.hcir_padded_dim(d)
+        self.idx_offset = int(idx_offset)
+        self.sm_count = _sm_count(self.device)
+        with torch.cuda.device(self.device):
+            self.g32 = torch.empty((n, self.ld), dtype=torch.float32, device=self.device)
+            self.gbf = torch.empty((n, self.ld), dtype=torch.bfloat16, device=self.device)
+            dmax = torch.zeros((), dtype=torch.float32, device=self.device)
+            for a in range(0, n, chunk_rows):
+                b = min(n, a + chunk_rows)
+                x = feats[a:b]
+                if not x.is_cuda:
+                    x = x.contiguous().to(self.device, non_blocking=True)
+                elif x.device != self.device:
+                    x = x.to(self.device)
+                if x.stride(1) != 1:
+                    x = x.contiguous()
+                dl = torch.empty((b - a,), dtype=torch.float32, device=self.device)
+                _lib.check(self.lib.hcir_l2norm_cast(x.data_ptr(), b - a, d, x.stride(0),
+                                                     self.g32[a:b].data_ptr(), self.gbf[a:b].data_ptr(),
+                                                     self.ld, dl.data_ptr(), _stream_ptr()), "l2norm_cast")
+                dmax = torch.maximum(dmax, dl.max())
+            self.g_delta_max = float(dmax.item())
+        # conservative bound on the tensor-core fp32 accumulation error + canonical-dot rounding
+        self.eps_acc = float(self.ld) * 2.0 ** -22
+        self.labels = None
+        self.classes_ = None
+        if labels is not None:
+            self.set_labels(labels, classes)
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------ labels
+    def set_labels(self, labels, classes=None):
+        y = labels.detach().cpu().numpy() if isinstance(labels, torch.Tensor) else np.asarray(labels)
+        y = y.reshape(-1)
+        if y.shape[0] != self.n:
+            raise ValueError(f"labels has {y.shape[0]} entries, gallery has {self.n} rows")
+        self.classes_ = np.unique(y) if classes is None else np.asarray(classes)
+        cls_idx = np.searchsorted(self.classes_, y)
+        if (cls_idx >= len(self.classes_)).any() or (self.classes_[np.minimum(cls_idx, len(self.classes_) - 1)] != y).any():
+            raise ValueError("labels contain values missing from `classes`")
+        self.labels = torch.from_numpy(cls_idx.astype(np.int32)).to(self.device)
+
+    # ------------------------------------------------------------------ planning
+    def choose_kc(self, k: int) -> int:
+        return 2 * k + 64
+
+    def use_tensor_path(self, nq: int, k: int) -> bool:
+        # tiny galleries are not worth a tcgen05 launch: the exact CUDA-core kernel is the path
+        return self.n >= max(4096, 8 * self.choose_kc(k))
+
+    # ------------------------------------------------------------------ search
+    def topk(self, queries, k: int, *, mode: str = "auto", return_device: bool = False):
+        """Exact cosine top-k: (sims [Q,k] fp32 descending, idx [Q,k] int64), canonical order
+        (ties -> ascending index).  ``mode``: "auto" | "tensor" | "exact"."""
+        q, kind = _as_2d_f32(queries, "queries")
+        if q.shape[1] != self.d:
+            raise ValueError(f"query dim {q.shape[1]} != gallery dim {self.d}")
+        k = int(k)
+        if not (1 <= k <= self.n):
+            raise ValueError(f"k={k} must be in [1, N={self.n}]")
+        with torch.cuda.device(self.device):
+            if not q.is_cuda:
+                q = q.contiguous().to(self.device, non_blocking=True)
+            elif q.device != self.device:
+                q = q.to(self.device)
+            sims, idx = self._topk_device(q, k, mode)
+            if return_device or kind == "torch_cuda":
+                return sims, idx
+            return _to_host(sims, kind), _to_host(idx, kind)
+
+    def _topk_device(self, q: torch.Tensor, k: int, mode: str = "auto"):
+        lib = self.lib
+        nq = q.shape[0]
+        dev = self.device
+        out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if nq == 0:
+            return out_sim, out_idx
+        if mode not in ("auto", "tensor", "exact"):
+            raise ValueError(f"unknown mode {mode!r}")
+        tensor = mode == "tensor" or (mode == "auto" and self.use_tensor_path(nq, k))
+        q32, qbf, qdl = l2_normalize(q, want_bf16=tensor, want_delta=tensor)
+        st = _stream_ptr()
+        if not tensor:
+            self._exact(q32, None, nq, k, out_sim, out_idx)
+            self.last_stats = {"path": "exact", "uncertified": 0}
+            return out_sim, out_idx
+        kc = self.choose_kc(k)
+        plan = Plan()
+        _lib.check(lib.hcir_simtopk_plan(nq, self.n, self.ld, kc, self.sm_count, plan), "simtopk_plan")
+        ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan,
+                                    ws.data_ptr(), st), "simtopk")
+        unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
+        unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.hcir_select_rescore(q32.data_ptr(), self.g32.data_ptr(), self.ld, nq, self.n, k,
+                                           self.idx_offset, plan, ws.data_ptr(), qdl.data_ptr(),
+                                           self.g_delta_max, self.eps_acc, out_sim.data_ptr(),
+                                           out_idx.data_ptr(), unc_list.data_ptr(), unc_cnt.data_ptr(), st),
+                   "select_rescore")
+        n_unc = int(unc_cnt.item())  # 4-byte readback: decides whether the exact fallback runs
+        if n_unc > 0:
+            self._exact(q32, unc_list, n_unc, k, out_sim, out_idx)
+        self.last_stats = {"path": "tensor", "uncertified": n_unc, "nsplit": int(plan.nsplit),
+                           "kc": int(plan.kc), "cap": int(plan.cap), "workspace_bytes": int(plan.bytes)}
+        return out_sim, out_idx
+
+    def _exact(self, q32, qlist, nlist, k, out_sim, out_idx):
+        lib = self.lib
+        nbytes = int(lib.hcir_exact_workspace_bytes(nlist, self.n, k, self.sm_count))
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        _lib.check(lib.hcir_exact_topk(q32.data_ptr(), self.g32.data_ptr(), self.ld, self.n, k,
+                                       self.idx_offset, qlist.data_ptr() if qlist is not None else None,
+                                       nlist, out_sim.data_ptr(), out_idx.data_ptr(), ws.data_ptr(), nbytes,
+                                       self.sm_count, _stream_ptr()), "exact_topk")
+
+    # ------------------------------------------------------------------ vote
+    def neighbour_labels(self, idx: torch.Tensor) -> torch.Tensor:
+        if self.labels is None:
+            raise ValueError("this GalleryBank was built without labels")
+        out = torch.empty(idx.shape, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.hcir_gather_labels(idx.data_ptr(), idx.numel(), self.labels.data_ptr(), self.n,
+                                               self.idx_offset, out.data_ptr(), _stream_ptr()), "gather_labels")
+        return out
+
+    def vote(self, sims: torch.Tensor, nbr_labels: torch.Tensor, *, T=None, return_scores: bool = False):
+        """K4 on device tensors: class INDEX [Q] int32 (+ optional [Q, C] scores)."""
+        nq, k = sims.shape
+        c = len(self.classes_)
+        pred = torch.empty((nq,), dtype=torch.int32, device=self.device)
+        scores = torch.empty((nq, c), dtype=torch.float32, device=self.device) if return_scores else None
+        _lib.check(self.lib.hcir_vote(sims.data_ptr(), nbr_labels.data_ptr(), nq, k, c,
+                                      float(T) if T is not None else 0.0, pred.data_ptr(),
+                                      scores.data_ptr() if return_scores else None, _stream_ptr()), "vote")
+        return (pred, scores) if return_scores else pred
+
+    def predict(self, queries, k: int, *, T=None, mode: str = "auto", return_neighbors: bool = False):
+        """kNN classification: predicted ORIGINAL label values [Q] int64.  ``T=None`` is the
+        reference's uniform vote; ``T>0`` the temperature-weighted extension."""
+        q, kind = _as_2d_f32(queries, "queries")
+        with torch.cuda.device(self.device):
+            if not q.is_cuda:
+                q = q.contiguous().to(self.device, non_blocking=True)
+            elif q.device != self.device:
+                q = q.to(self.device)
+            sims, idx = self._topk_device(q, int(k), mode)
+            pred_idx = self.vote(sims, self.neighbour_labels(idx), T=T)
+            cls = torch.from_numpy(self.classes_.astype(np.int64)).to(self.device)
+            pred = cls[pred_idx.long()]
+            if return_neighbors:
+                return _to_host(pred, kind), _to_host(sims, kind), _to_host(idx, kind)
+            return _to_host(pred, kind)
+
+    def predict_multi_k(self, queries, ks, *, T=None, mode: str = "auto"):
+        """One search at max(ks), one prefix vote per k (the reference recomputes the whole
+        distance matrix per k: classification_engine.py:79-82).  Returns {k: pred [Q]}."""
+        ks = [int(k) for k in ks]
+        q, kind = _as_2d_f32(queries, "queries")
+        with torch.cuda.device(self.device):
+            if not q.is_cuda:
+                q = q.contiguous().to(self.device, non_blocking=True)
+            elif q.device != self.device:
+                q = q.to(self.device)
+            sims, idx = self._topk_device(q, max(ks), mode)
+            nl = self.neighbour_labels(idx)
+            cls = torch.from_numpy(self.classes_.astype(np.int64)).to(self.device)
+            out = {}
+            for k in ks:
+                p = self.vote(sims[:, :k].contiguous(), nl[:, :k].contiguous(), T=T)
+                out[k] = _to_host(cls[p.long()], kind)
+            return out
+
+
+# ---------------------------------------------------------------------------------------------
+# functional surface
+# ---------------------------------------------------------------------------------------------
+def knn_topk(bank, query, k, *, mode: str = "auto"):
+    """``torch.mm(query_n, bank_n.t()).topk(k)`` (qualitative_test.py:79-84;
+    dual_view_model.py:317-335) without materialising the similarity matrix.
+    ``bank`` is a [N, D] array/tensor or a prepared :class:`GalleryBank`."""
+    gb = bank if isinstance(bank, GalleryBank) else GalleryBank(bank)
+    return gb.topk(query, k, mode=mode)
+
+
+def knn_predict(query, bank, labels, k, *, T=None, mode: str = "auto"):
+    """kNN classification of ``query`` against (``bank``, ``labels``): uniform vote (T=None,
+    == classification_engine.py:80-82) or temperature-weighted vote (T>0, extension)."""
+    gb = bank if isinstance(bank, GalleryBank) else GalleryBank(bank, labels)
+    if gb.labels is None:
+        gb.set_labels(labels)
+    return gb.predict(query, k, T=T, mode=mode)

@@ -1,0 +1,134 @@
+"""Multi-GPU: the gallery is row-sharded over the ranks of one box (one process per GPU,
+``torch.distributed``; NCCL over NVLink on GPUs).  Each rank computes its exact local top-k,
+ONE all-gather of k candidates per query per rank follows, and a merge kernel (K5) produces
+the global top-k on every rank (no reference analogue -- the
+reference's kNN is single-process CPU, classification_engine.py:51,63).
+
+``ShardPlan`` and ``exchange_candidates`` are backend-agnostic (tested with gloo on CPU);
+the local search and the merge are CUDA-only."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import GalleryBank, _as_2d_f32, _stream_ptr, _to_host
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Contiguous row partition: rank r owns rows [start(r), stop(r)); the first ``n % world``
+    ranks hold one extra row."""
+    n: int
+    world: int
+
+    def start(self, r: int) -> int:
+        base, extra = divmod(self.n, self.world)
+        return r * base + min(r, extra)
+
+    def stop(self, r: int) -> int:
+        return self.start(r + 1) if r + 1 < self.world else self.n
+
+    def size(self, r: int) -> int:
+        return self.stop(r) - self.start(r)
+
+    def owner(self, row: int) -> int:
+        base, extra = divmod(self.n, self.world)
+        pivot = extra * (base + 1)
+        return row // (base + 1) if row < pivot else extra + (row - pivot) // max(base, 1)
+
+
+def exchange_candidates(sims: torch.Tensor, idx: torch.Tensor, labels: torch.Tensor | None = None,
+                        group=None):
+    """The path's single collective: all-gather every rank's [Q, k] exact local top-k
+    (fp32 sims, int64 global indices, optional int32 labels) -> [G, Q, k] on every rank."""
+    world = dist.get_world_size(group)
+    g_sims = torch.empty((world,) + tuple(sims.shape), dtype=sims.dtype, device=sims.device)
+    g_idx = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(g_sims, sims.contiguous(), group=group)
+    dist.all_gather_into_tensor(g_idx, idx.contiguous(), group=group)
+    g_lab = None
+    if labels is not None:
+        g_lab = torch.empty((world,) + tuple(labels.shape), dtype=labels.dtype, device=labels.device)
+        dist.all_gather_into_tensor(g_lab, labels.contiguous(), group=group)
+    return g_sims, g_idx, g_lab
+
+
+def merge_topk(g_sims: torch.Tensor, g_idx: torch.Tensor, g_lab: torch.Tensor | None, k: int):
+    """K5 on device: canonical top-k of the union of G canonical lists."""
+    lib = _lib.load()
+    G, nq, kk = g_sims.shape
+    dev = g_sims.device
+    out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_lab = torch.empty((nq, k), dtype=torch.int32, device=dev) if g_lab is not None else None
+    if kk != k:
+        raise ValueError("merge_topk expects per-shard lists of width k")
+    with torch.cuda.device(dev):
+        _lib.check(lib.hcir_merge_topk(g_sims.data_ptr(), g_idx.data_ptr(),
+                                       g_lab.data_ptr() if g_lab is not None else None, G, nq, k,
+                                       out_sim.data_ptr(), out_idx.data_ptr(),
+                                       out_lab.data_ptr() if out_lab is not None else None, _stream_ptr()),
+                   "merge_topk")
+    return out_sim, out_idx, out_lab
+
+
+class ShardedGallery:
+    """Rank-local shard of a global gallery + the exchange/merge step.
+
+    ``features_local`` are THIS rank's rows [plan.start(rank), plan.stop(rank)); queries are
+    replicated on every rank.  Results are identical on every rank and bit-identical to the
+    single-GPU result (local lists are exact fp32 canonical lists, the merge is a pure
+    sort-merge on (sim desc, idx asc))."""
+
+    def __init__(self, features_local, labels_local=None, *, n_total: int, group=None, device=None,
+                 classes=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.plan = ShardPlan(int(n_total), self.world)
+        if n_total >= (1 << 32) - 1:
+            raise ValueError("global gallery must hold fewer than 2^32 - 1 rows")
+        feats, _ = _as_2d_f32(features_local, "features_local")
+        if feats.shape[0] != self.plan.size(self.rank):
+            raise ValueError(f"rank {self.rank}: got {feats.shape[0]} rows, plan says {self.plan.size(self.rank)}")
+        self.bank = GalleryBank(feats, labels_local, device=device, idx_offset=self.plan.start(self.rank),
+                                classes=classes)
+        self.device = self.bank.device
+
+    def _local(self, q: torch.Tensor, k: int, mode: str):
+        """Exact local top-min(k, n_local), padded to width k with (-inf, -1)."""
+        kl = min(k, self.bank.n)
+        sims, idx = self.bank._topk_device(q, kl, mode)
+        if kl < k:
+            pad_s = torch.full((q.shape[0], k - kl), float("-inf"), dtype=torch.float32, device=self.device)
+            pad_i = torch.full((q.shape[0], k - kl), -1, dtype=torch.int64, device=self.device)
+            sims, idx = torch.cat([sims, pad_s], 1), torch.cat([idx, pad_i], 1)
+        return sims, idx
+
+    def topk(self, queries, k: int, *, mode: str = "auto", with_labels: bool = False):
+        q, kind = _as_2d_f32(queries, "queries")
+        with torch.cuda.device(self.device):
+            if not q.is_cuda:
+                q = q.contiguous().to(self.device, non_blocking=True)
+            sims, idx = self._local(q, int(k), mode)
+            lab = self.bank.neighbour_labels(idx) if with_labels else None
+            g_s, g_i, g_l = exchange_candidates(sims, idx, lab, self.group)
+            o_s, o_i, o_l = merge_topk(g_s, g_i, g_l, int(k))
+        if with_labels:
+            return o_s, o_i, o_l
+        if kind == "torch_cuda":
+            return o_s, o_i
+        return _to_host(o_s, kind), _to_host(o_i, kind)
+
+    def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
+        _, kind = _as_2d_f32(queries, "queries")
+        o_s, o_i, o_l = self.topk(queries, k, mode=mode, with_labels=True)
+        with torch.cuda.device(self.device):
+            pred_idx = self.bank.vote(o_s, o_l, T=T)
+            cls = torch.from_numpy(np.asarray(self.bank.classes_).astype(np.int64)).to(self.device)
+            pred = cls[pred_idx.long()]
+        return _to_host(pred, kind)

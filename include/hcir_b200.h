@@ -1,0 +1,144 @@
+/* hcir_b200 -- C ABI of the B200-native exact cosine top-k / kNN-vote path.
+ *
+ * The reference (atunnd/Hair-centric-Image-Retrieval) has no FFI of its own: its hot path is
+ * a Python call surface that hands dense matrices to sklearn / numpy / torch.  Each entry
+ * point below replaces one of those library calls; the reference file:line it stands in for
+ * is cited on the declaration.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *   - the caller owns all buffers, including workspaces; the library allocates nothing and
+ *     keeps no state except a thread-local last-error string;
+ *   - kernels are enqueued on `stream` and the call returns immediately (asynchronous);
+ *   - return value: HCIR_OK (0) or a negative HCIR_E* code; hcir_last_error() explains it;
+ *   - there is NO CPU fallback and no other backend: on a device that is not sm_100 every
+ *     compute entry point fails with HCIR_EARCH.
+ *   - internal bank layout: row-major, row stride `ld` = D rounded up to a multiple of 64
+ *     elements, zero padded (hcir_padded_dim()).  fp32 bank + bf16 bank of the same `ld`.
+ *   - a candidate KEY (uint64) = order-preserving bits of the fp32 similarity << 32
+ *     | (0xFFFFFFFF - gallery row).  Larger key = better (desc. similarity, asc. index).
+ *   - gallery shards hold fewer than 2^31 rows; the global index space is < 2^32 - 1.
+ */
+#ifndef HCIR_B200_H_
+#define HCIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCIR_OK 0
+#define HCIR_EINVAL (-1)     /* bad shape / alignment / k > N / null pointer              */
+#define HCIR_EARCH (-2)      /* current device is not sm_100 (B200)                        */
+#define HCIR_ECUDA (-3)      /* a CUDA runtime / driver call failed                        */
+#define HCIR_EWORKSPACE (-4) /* workspace too small                                        */
+
+#define HCIR_ABI_VERSION 1
+
+typedef void* hcir_stream_t; /* cudaStream_t */
+
+int hcir_abi_version(void);
+const char* hcir_last_error(void);
+/* 1 if the current device can run the kernels (compute capability 10.x), else 0. */
+int hcir_device_supported(void);
+/* D rounded up to the internal row stride (multiple of 64). */
+int hcir_padded_dim(int d);
+
+/* K1 -- fused row L2-normalise (+ cast).  Replaces torch.nn.functional.normalize(f, dim=1)
+ * at HairPretraining/src/classification_engine.py:50,62 and qualitative_test.py:57,76, the
+ * sklearn `normalize` inside cosine_similarity (src/models/hair_encoder.py:193) and
+ * faiss.normalize_L2 (HairPretraining/app/inference.py:75,90).
+ *   x        [n, d]  fp32, row stride ldx (elements)
+ *   out_f32  [n, ld] fp32 unit rows, zero padded          (nullable)
+ *   out_bf16 [n, ld] bf16 unit rows, zero padded          (nullable, uint16 storage)
+ *   out_delta[n]     || unit_row - float(bf16(unit_row)) ||_2  (nullable; feeds the
+ *                    certification bound of hcir_select_rescore)
+ * y = x / max(||x||_2, 1e-12). */
+int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, float* out_f32,
+                     uint16_t* out_bf16, int ld, float* out_delta, hcir_stream_t stream);
+
+/* K2 -- similarity contraction fused with a running top-kc.  Replaces
+ * torch.mm(q, G.t()) (qualitative_test.py:79, dual_view_model.py:333), the sgemm inside
+ * sklearn's pairwise cosine (classification_engine.py:82; hair_encoder.py:193) and faiss
+ * IndexFlatL2.search (inference.py:108) together with the N-wide partial sort that follows
+ * them.  bf16 x bf16 -> fp32 on tcgen05 tensor cores (TMA-fed, accumulators in TMEM); the
+ * [nq, ng] similarity matrix is never written to memory.  Output: for every query and
+ * every gallery split a list of at most `kc` candidate KEYS (bf16-contraction scores) such
+ * that every gallery row NOT listed scores <= the kc-th best listed score of that query.
+ *
+ * hcir_simtopk_plan fills the launch plan: number of gallery splits, list capacity and the
+ * workspace size.  Workspace layout: int32 counts[nq][nsplit]; uint64 keys[nq][nsplit][cap]. */
+typedef struct {
+  int32_t nsplit;      /* gallery splits (one candidate list per query per split)       */
+  int32_t cap;         /* capacity of one candidate list (>= kc + 64)                   */
+  int32_t kc;          /* candidates kept per list                                      */
+  int32_t reserved;
+  uint64_t counts_off; /* byte offset of counts[] in the workspace                      */
+  uint64_t keys_off;   /* byte offset of keys[] in the workspace                        */
+  uint64_t bytes;      /* total workspace bytes                                         */
+} hcir_plan_t;
+
+int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_count, hcir_plan_t* plan);
+int hcir_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng, int ld,
+                 const hcir_plan_t* plan, void* workspace, hcir_stream_t stream);
+/* Debug / test entry: same kernel, additionally dumps the raw fp32 accumulator tile values
+ * to scores[nq][ng] (row-major).  Only for small problems. */
+int hcir_simtopk_debug(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng,
+                       int ld, const hcir_plan_t* plan, void* workspace, float* scores,
+                       hcir_stream_t stream);
+
+/* K3 -- candidate selection + fp32 re-score + exact sort + certification.  Replaces
+ * torch.topk(sim, k) (qualitative_test.py:82), np.argsort(s)[::-1][:k]
+ * (hair_encoder.py:194) and sklearn's argpartition+argsort (_kneighbors_reduce_func).
+ * Per query: merge the split lists, keep the kc best by bf16 score, re-score with the
+ * canonical fp32 dot product only the candidates that can still reach the top-k, emit the
+ * exact top-k in canonical order, and certify it:
+ *     certified <=> (all gallery rows were candidates) or
+ *                   fp32_score(k-th) > bf16_score(kc-th) + eps(query)
+ *     eps = g_delta_max*(1+q_delta) + q_delta*(1+1e-6) + eps_acc
+ * Uncertified queries are appended to uncert_list / *uncert_count for hcir_exact_topk.
+ *   out_sim [nq,k] fp32 descending, out_idx [nq,k] int64 (= local row + idx_offset). */
+int hcir_select_rescore(const float* q_f32, const float* g_f32, int ld, int64_t nq, int64_t ng,
+                        int k, int64_t idx_offset, const hcir_plan_t* plan, const void* workspace,
+                        const float* q_delta, float g_delta_max, float eps_acc, float* out_sim,
+                        int64_t* out_idx, int32_t* uncert_list, int32_t* uncert_count,
+                        hcir_stream_t stream);
+
+/* Exact fp32 path (CUDA cores): brute-force canonical fp32 similarities + exact top-k in
+ * canonical order for the queries listed in qlist[0..nlist) (qlist == NULL: queries
+ * 0..nlist-1).  It is the GPU fallback for uncertified queries and the whole path when the
+ * problem is too small for the tensor-core kernel.  Rows of out_* are indexed by query id.
+ * Workspace: hcir_exact_workspace_bytes(nlist, ng, k). */
+size_t hcir_exact_workspace_bytes(int64_t nlist, int64_t ng, int k, int sm_count);
+int hcir_exact_topk(const float* q_f32, const float* g_f32, int ld, int64_t ng, int k,
+                    int64_t idx_offset, const int32_t* qlist, int64_t nlist, float* out_sim,
+                    int64_t* out_idx, void* workspace, size_t workspace_bytes, int sm_count,
+                    hcir_stream_t stream);
+
+/* Neighbour label gather: out[q][j] = labels[idx[q][j] - idx_offset]  (labels are class
+ * indices 0..C-1, i.e. sklearn's `_y`, HairPretraining/src/classification_engine.py:81). */
+int hcir_gather_labels(const int64_t* idx, int64_t count, const int32_t* labels, int64_t n_labels,
+                       int64_t idx_offset, int32_t* out, hcir_stream_t stream);
+
+/* K4 -- kNN vote.  T <= 0: uniform majority vote == sklearn `_mode(_y[neigh_ind])`
+ * (classification_engine.py:82 -> neighbors/_classification.py:299-307), ties -> smallest
+ * class.  T > 0: EXTENSION (not in the reference), score[c] = sum_j exp((s_j - s_0)/T) over
+ * neighbours of class c in rank order, arg-max, ties -> smallest class.
+ *   sims [nq,k] fp32, nbr_labels [nq,k] int32 in [0,num_classes)
+ *   pred [nq] int32 class index; scores [nq,num_classes] fp32 (nullable). */
+int hcir_vote(const float* sims, const int32_t* nbr_labels, int64_t nq, int k, int num_classes,
+              float T, int32_t* pred, float* scores, hcir_stream_t stream);
+
+/* K5 -- merge of per-shard exact top-k lists after the all-gather (new design, no reference
+ * analogue).  gathered_* are [G][nq][k] with every [g][q][:] list in
+ * canonical order; output the canonical top-k of the union.  Labels are optional. */
+int hcir_merge_topk(const float* gathered_sim, const int64_t* gathered_idx,
+                    const int32_t* gathered_lab, int G, int64_t nq, int k, float* out_sim,
+                    int64_t* out_idx, int32_t* out_lab, hcir_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCIR_B200_H_ */

@@ -1,0 +1,119 @@
+"""CPU: the C-ABI library builds/loads, exports every symbol include/hcir_b200.h declares,
+argument validation works without a GPU, and compute fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hcir_b200
+from hcir_b200 import _lib, _build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_loads():
+    lib = _lib.load()
+    assert os.path.exists(_build.LIB_PATH)
+    assert lib.hcir_abi_version() == 1
+    assert lib.hcir_padded_dim(768) == 768 and lib.hcir_padded_dim(512) == 512
+    assert lib.hcir_padded_dim(100) == 128 and lib.hcir_padded_dim(2048) == 2048
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "hcir_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hcir_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_build.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in hcir_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_sass_is_blackwell_native():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _build.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, f"{mnemonic} missing: simtopk is not a tcgen05/TMA kernel"
+    assert "HGMMA" not in sass
+
+
+def test_plan_is_consistent():
+    lib = _lib.load()
+    p = _lib.Plan()
+    for nq, ng, ld, kc in [(10000, 200000, 768, 104), (1, 5000, 768, 104), (64, 10_000_000, 768, 104),
+                           (16384, 1_250_000, 2048, 464), (129, 257, 64, 74), (4096, 1_000_000, 768, 264)]:
+        assert lib.hcir_simtopk_plan(nq, ng, ld, kc, 148, p) == 0
+        tiles = -(-ng // 256)
+        tps = -(-tiles // p.nsplit)
+        assert -(-tiles // tps) == p.nsplit, "empty split"
+        assert p.cap >= p.kc + 64 and p.cap % 32 == 0
+        assert p.nsplit * p.kc <= 16384 or p.nsplit == 1
+        assert p.bytes >= p.keys_off + nq * p.nsplit * p.cap * 8
+    assert lib.hcir_simtopk_plan(0, 10, 64, 10, 148, p) == _lib.HCIR_EINVAL
+    assert "bad shape" in _lib.last_error()
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    # ld must equal padded dim -> EINVAL before any CUDA call
+    assert lib.hcir_l2norm_cast(None, 4, 100, 100, None, None, 100, None, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_vote(None, None, 4, 0, 3, 0.0, None, None, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_merge_topk(None, None, None, 0, 4, 5, None, None, None, None) == _lib.HCIR_EINVAL
+    with pytest.raises(ValueError):
+        _lib.check(lib.hcir_exact_topk(None, None, 100, 10, 5, 0, None, 1, None, None, None, 0, 148, None), "x")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.hcir_device_supported() == 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hcir_b200.GalleryBank(np.random.randn(16, 8).astype(np.float32))
+    with pytest.raises(RuntimeError):
+        hcir_b200.KNeighborsClassifierB200(3).fit(np.random.randn(16, 8).astype(np.float32), np.arange(16))
+    # a well-formed compute call on a box without a B200 must fail, not compute
+    x = np.zeros((4, 64), np.float32)
+    rc = lib.hcir_l2norm_cast(x.ctypes.data, 4, 64, 64, None, None, 64, None, None)
+    assert rc in (_lib.HCIR_ECUDA, _lib.HCIR_EARCH)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "hair-centric-image-retrieval_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert not re.search(r"^\s*(from|import)\s+sklearn", src, flags=re.M), f
+
+
+def test_shard_plan():
+    from hcir_b200 import ShardPlan
+    for n, w in [(10, 3), (1_000_000, 8), (7, 8), (64, 2), (10_000_001, 8)]:
+        sp = ShardPlan(n, w)
+        assert sp.start(0) == 0 and sp.stop(w - 1) == n
+        assert sum(sp.size(r) for r in range(w)) == n
+        for r in range(w - 1):
+            assert sp.stop(r) == sp.start(r + 1)
+        for row in {0, n - 1, n // 2, n // 3}:
+            r = sp.owner(row)
+            assert sp.start(r) <= row < sp.stop(r)
+
+
+def test_classifier_argument_validation():
+    from hcir_b200 import KNeighborsClassifierB200
+    with pytest.raises(ValueError):
+        KNeighborsClassifierB200(5, metric="euclidean")
+    with pytest.raises(ValueError):
+        KNeighborsClassifierB200(5, weights="distance")
+    with pytest.raises(RuntimeError):
+        KNeighborsClassifierB200(5).predict(np.zeros((2, 4), np.float32))
