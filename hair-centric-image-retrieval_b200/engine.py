@@ -141,6 +141,21 @@ class GalleryBank:
         if labels is not None:
             self.set_labels(labels, classes)
         self.last_stats = {}
+        # bench.py sets this to a list to get (name, start_event, end_event) per kernel launch
+        self.kernel_events = None
+        self.launches = 0  # number of hcir kernels launched by this bank since construction
+
+    def _timed(self, name, fn, n_kernels=1):
+        """Run one C-ABI launch; optionally bracket it with CUDA events on the current stream."""
+        self.launches += n_kernels
+        if self.kernel_events is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn()
+        b.record()
+        self.kernel_events.append((name, a, b))
+        return rc
 
     # ------------------------------------------------------------------ labels
     def set_labels(self, labels, classes=None):
@@ -194,6 +209,7 @@ class GalleryBank:
             raise ValueError(f"unknown mode {mode!r}")
         tensor = mode == "tensor" or (mode == "auto" and self.use_tensor_path(nq, k))
         q32, qbf, qdl = l2_normalize(q, want_bf16=tensor, want_delta=tensor)
+        self.launches += 1
         st = _stream_ptr()
         if not tensor:
             self._exact(q32, None, nq, k, out_sim, out_idx)
@@ -203,15 +219,14 @@ class GalleryBank:
         plan = Plan()
         _lib.check(lib.hcir_simtopk_plan(nq, self.n, self.ld, kc, self.sm_count, plan), "simtopk_plan")
         ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
-        _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan,
-                                    ws.data_ptr(), st), "simtopk")
+        _lib.check(self._timed("simtopk", lambda: lib.hcir_simtopk(
+            qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan, ws.data_ptr(), st)), "simtopk")
         unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
         unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _lib.check(lib.hcir_select_rescore(q32.data_ptr(), self.g32.data_ptr(), self.ld, nq, self.n, k,
-                                           self.idx_offset, plan, ws.data_ptr(), qdl.data_ptr(),
-                                           self.g_delta_max, self.eps_acc, out_sim.data_ptr(),
-                                           out_idx.data_ptr(), unc_list.data_ptr(), unc_cnt.data_ptr(), st),
-                   "select_rescore")
+        _lib.check(self._timed("select_rescore", lambda: lib.hcir_select_rescore(
+            q32.data_ptr(), self.g32.data_ptr(), self.ld, nq, self.n, k, self.idx_offset, plan, ws.data_ptr(),
+            qdl.data_ptr(), self.g_delta_max, self.eps_acc, out_sim.data_ptr(), out_idx.data_ptr(),
+            unc_list.data_ptr(), unc_cnt.data_ptr(), st)), "select_rescore")
         n_unc = int(unc_cnt.item())  # 4-byte readback: decides whether the exact fallback runs
         if n_unc > 0:
             self._exact(q32, unc_list, n_unc, k, out_sim, out_idx)
@@ -223,16 +238,17 @@ class GalleryBank:
         lib = self.lib
         nbytes = int(lib.hcir_exact_workspace_bytes(nlist, self.n, k, self.sm_count))
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
-        _lib.check(lib.hcir_exact_topk(q32.data_ptr(), self.g32.data_ptr(), self.ld, self.n, k,
-                                       self.idx_offset, qlist.data_ptr() if qlist is not None else None,
-                                       nlist, out_sim.data_ptr(), out_idx.data_ptr(), ws.data_ptr(), nbytes,
-                                       self.sm_count, _stream_ptr()), "exact_topk")
+        _lib.check(self._timed("exact_topk", lambda: lib.hcir_exact_topk(
+            q32.data_ptr(), self.g32.data_ptr(), self.ld, self.n, k, self.idx_offset,
+            qlist.data_ptr() if qlist is not None else None, nlist, out_sim.data_ptr(), out_idx.data_ptr(),
+            ws.data_ptr(), nbytes, self.sm_count, _stream_ptr()), n_kernels=2), "exact_topk")
 
     # ------------------------------------------------------------------ vote
     def neighbour_labels(self, idx: torch.Tensor) -> torch.Tensor:
         if self.labels is None:
             raise ValueError("this GalleryBank was built without labels")
         out = torch.empty(idx.shape, dtype=torch.int32, device=self.device)
+        self.launches += 1
         _lib.check(self.lib.hcir_gather_labels(idx.data_ptr(), idx.numel(), self.labels.data_ptr(), self.n,
                                                self.idx_offset, out.data_ptr(), _stream_ptr()), "gather_labels")
         return out
@@ -243,6 +259,7 @@ class GalleryBank:
         c = len(self.classes_)
         pred = torch.empty((nq,), dtype=torch.int32, device=self.device)
         scores = torch.empty((nq, c), dtype=torch.float32, device=self.device) if return_scores else None
+        self.launches += 1
         _lib.check(self.lib.hcir_vote(sims.data_ptr(), nbr_labels.data_ptr(), nq, k, c,
                                       float(T) if T is not None else 0.0, pred.data_ptr(),
                                       scores.data_ptr() if return_scores else None, _stream_ptr()), "vote")
