@@ -58,6 +58,14 @@ __device__ __forceinline__ uint64_t make_key(float sim, uint32_t idx) {
   return (static_cast<uint64_t>(f2ord(sim)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
 }
 __device__ __forceinline__ float key_sim(uint64_t key) { return ord2f(static_cast<uint32_t>(key >> 32)); }
+// RAW key (what the simtopk epilogue appends: fp32 bits << 32 | ~index) <-> ordered key
+__device__ __forceinline__ uint64_t raw2key(uint64_t raw) {
+  return (static_cast<uint64_t>(f2ord(__uint_as_float(static_cast<uint32_t>(raw >> 32)))) << 32) |
+         (raw & 0xFFFFFFFFull);
+}
+__device__ __forceinline__ uint64_t key2raw(uint64_t key) {
+  return (static_cast<uint64_t>(__float_as_uint(key_sim(key))) << 32) | (key & 0xFFFFFFFFull);
+}
 __device__ __forceinline__ uint32_t key_idx(uint64_t key) { return 0xFFFFFFFFu - static_cast<uint32_t>(key); }
 
 // ---- canonical fp32 dot product ----------------------------------------------------------
@@ -86,7 +94,13 @@ __device__ __forceinline__ float canonical_dot(const float4* __restrict__ q4,
 // GLOBAL memory (L2 resident) -- compacted in place to buf[0..keep) in arbitrary order.
 // Returns the keep-th largest key.  MSB-first radix select, 8-bit digits; `hist` is a
 // per-warp shared-memory scratch of 256 words.  All 32 lanes must call it convergently.
+// kRaw: the buffer holds RAW keys (see raw2key); the returned threshold is an ordered key.
+template <bool kRaw = false>
 __device__ inline uint64_t warp_prune(uint64_t* buf, int cnt, int keep, uint32_t* hist, int lane) {
+  auto load = [&](int i) -> uint64_t {
+    const uint64_t x = __ldcg(buf + i);
+    return kRaw ? raw2key(x) : x;
+  };
   uint64_t prefix = 0, mask = 0;
   uint32_t remaining = static_cast<uint32_t>(keep);
   __syncwarp();
@@ -94,7 +108,7 @@ __device__ inline uint64_t warp_prune(uint64_t* buf, int cnt, int keep, uint32_t
     for (int b = lane; b < 256; b += kWarp) hist[b] = 0;
     __syncwarp();
     for (int i = lane; i < cnt; i += kWarp) {
-      const uint64_t key = __ldcg(buf + i);
+      const uint64_t key = load(i);
       if ((key & mask) == prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & 0xFFu], 1u);
     }
     __syncwarp();
@@ -137,7 +151,7 @@ __device__ inline uint64_t warp_prune(uint64_t* buf, int cnt, int keep, uint32_t
       // exactly one key carries this prefix: it IS the keep-th largest; fetch it and stop.
       uint64_t found = 0;
       for (int i = lane; i < cnt; i += kWarp) {
-        const uint64_t key = __ldcg(buf + i);
+        const uint64_t key = load(i);
         if ((key & mask) == prefix) found = key;
       }
 #pragma unroll
@@ -150,11 +164,11 @@ __device__ inline uint64_t warp_prune(uint64_t* buf, int cnt, int keep, uint32_t
   int out = 0;
   for (int base = 0; base < cnt; base += kWarp) {
     const int i = base + lane;
-    const uint64_t key = (i < cnt) ? __ldcg(buf + i) : 0ull;
+    const uint64_t key = (i < cnt) ? load(i) : 0ull;
     const bool keepit = (i < cnt) && (key >= thr);
     const uint32_t b = __ballot_sync(kFull, keepit);
     __syncwarp();
-    if (keepit) buf[out + __popc(b & ((1u << lane) - 1u))] = key;
+    if (keepit) buf[out + __popc(b & ((1u << lane) - 1u))] = kRaw ? key2raw(key) : key;
     out += __popc(b);
     __syncwarp();
   }

@@ -15,6 +15,7 @@
 //   warps 4-7 epilogue         (128 threads = 128 TMEM lanes = 128 query rows)
 // Work item = (query tile of 128 rows) x (gallery split = contiguous range of 256-row tiles).
 #include <cuda.h>
+#include <math.h>
 
 #include "hcir_common.cuh"
 #include "hcir_ptx.cuh"
@@ -38,35 +39,55 @@ constexpr size_t kSimSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kSta
 
 struct SimParams {
   int64_t nq, ng;
-  int ld, num_kb, num_qt, tiles_total, tiles_per_split, nsplit, cap, kc, num_items;
-  int32_t* counts;
-  uint64_t* keys;
-  float* dump;
+  int ld, num_kb, num_qt, tiles_total, tiles_per_split, nsplit, cap, kc, num_items, flags;
+  int32_t* counts;    // [nq][nsplit]      main: candidates per list
+  uint64_t* keys;     // [nq][nsplit][cap] main: candidate keys
+  const float* thr0;  // [nq] or null      main: initial per-query threshold (from the sample pass)
+  float* thr_out;     // [nq][nsplit]      main: threshold each list ended with
+  float* dump;        // [nq][ng]          debug: raw accumulator values
+  float* cmax;        // [nq][num_chunks]  sample: maxima of `chunk_w` consecutive sample columns
+  int chunk_w, num_chunks;
 };
 
-// Scan one 32-column chunk of accumulator values for one query row.
+enum : int { kModeMain = 0, kModeDump = 1, kModeSample = 2 };
+
+// Scan one 32-column chunk of accumulator values: lane = query row, v[j] = column gcol0 + j.
+// Survivors (value > the row's threshold) are appended to the row's list as RAW keys
+// (fp32 bits << 32 | ~index; consumers apply the order-preserving transform on load).
+// The epilogue warp is alone on its scheduler, so what matters is the dependent-instruction
+// chain, not the instruction count: after one warp-wide vote that skips chunks without any
+// survivor, the code is branch-free -- 32 independent compare / predicated-store groups whose
+// only serial dependency is the list cursor.
 template <bool kBounded>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, uint64_t* buf, int& cnt,
                                            uint32_t gcol0, int lim) {
-  bool any = false;
+  float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const bool hit = __uint_as_float(v[j]) > thr;
-    any |= kBounded ? (hit && j < lim) : hit;
+    const float f = __uint_as_float(v[j]);
+    mx = fmaxf(mx, (kBounded && j >= lim) ? -INFINITY : f);
   }
-  if (any) {
+  if (!__any_sync(kFull, mx > thr)) return;
+  uint64_t* dst = buf + cnt;
+  const uint32_t inv0 = 0xFFFFFFFFu - gcol0;
+  int c = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float f = __uint_as_float(v[j]);
-      if ((f > thr) && (!kBounded || j < lim)) {
-        buf[cnt] = make_key(f, gcol0 + j);
-        ++cnt;
-      }
-    }
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t hit = ((__uint_as_float(v[j]) > thr) && (!kBounded || j < lim)) ? 1u : 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p st.global.v2.b32 [%1], {%2, %3};\n\t"
+        "}" ::"r"(hit),
+        "l"(dst + c), "r"(inv0 - j), "r"(v[j])
+        : "memory");
+    c += hit;
   }
+  cnt += c;
 }
 
-template <bool kDump>
+template <int kMode>
 __global__ void __launch_bounds__(kSimThreads, 1)
 simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                const SimParams p) {
@@ -162,86 +183,170 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: TMEM -> threshold filter -> candidate lists =====================
+    // ===================== epilogue =====================
     const int ew = warp - kEpiWarp0;  // == warp % 4: the TMEM lane quarter this warp may read
-    uint32_t* hist = hist_all + ew * 256;
     const int row = ew * 32 + lane;
-    const int prune_at = p.cap - 32;
     uint32_t iter = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int split = item / p.num_qt, qt = item - split * p.num_qt;
-      const int t0 = split * p.tiles_per_split;
-      const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
-      const int64_t q = static_cast<int64_t>(qt) * kBlockM + row;
-      const bool active = q < p.nq;
-      float thr = active ? -INFINITY : INFINITY;
-      int cnt = 0;
-      uint64_t* buf = p.keys + (active ? (q * p.nsplit + split) * static_cast<int64_t>(p.cap) : 0);
-      for (int t = t0; t < t1; ++t, ++iter) {
-        const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
-        ptx::mbar_wait(&tfull_bar[acc], aphase);
-        ptx::tc_fence_after();
-        const int64_t gbase = static_cast<int64_t>(t) * kBlockN;
-        const bool full_tile = gbase + kBlockN <= p.ng;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
-          ptx::tmem_ld_wait();
-          if (c == kBlockN / 32 - 1) {
-            // whole accumulator stage is in registers now: hand it back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-          }
-          const uint32_t gcol0 = static_cast<uint32_t>(gbase) + c * 32;
-          if (full_tile) {
-            scan_chunk<false>(v, thr, buf, cnt, gcol0, 32);
-          } else {
-            const int64_t rem = p.ng - static_cast<int64_t>(gcol0);
-            const int lim = rem >= 32 ? 32 : (rem > 0 ? static_cast<int>(rem) : 0);
-            scan_chunk<true>(v, thr, buf, cnt, gcol0, lim);
-          }
-          if (kDump && active) {
+    if constexpr (kMode == kModeSample) {
+      // ---- sample pass: maxima of chunk_w consecutive sample columns, no per-row state ----
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int split = item / p.num_qt, qt = item - split * p.num_qt;
+        const int t0 = split * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        const int64_t q = static_cast<int64_t>(qt) * kBlockM + row;
+        const bool active = q < p.nq;
+        for (int t = t0; t < t1; ++t, ++iter) {
+          const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
+          ptx::mbar_wait(&tfull_bar[acc], aphase);
+          ptx::tc_fence_after();
+          const int64_t gbase = static_cast<int64_t>(t) * kBlockN;
+          const bool full_tile = gbase + kBlockN <= p.ng;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN;
+          float m8[kBlockN / 8];  // maxima of 8-column groups of this tile
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t g = static_cast<int64_t>(gcol0) + j;
-              if (g < p.ng) p.dump[q * p.ng + g] = __uint_as_float(v[j]);
+          for (int c = 0; c < kBlockN / 32; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            if (c == kBlockN / 32 - 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            }
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float m = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float f = __uint_as_float(v[g8 * 8 + j]);
+                if (!full_tile && gbase + c * 32 + g8 * 8 + j >= p.ng) f = -INFINITY;
+                m = fmaxf(m, f);
+              }
+              m8[c * 4 + g8] = m;
             }
           }
-          // lists that could overflow during the next chunk are pruned back to kc now
-          uint32_t need = __ballot_sync(kFull, cnt > prune_at);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const uint64_t bptr = __shfl_sync(kFull, reinterpret_cast<uint64_t>(buf), src);
-            const int bcnt = __shfl_sync(kFull, cnt, src);
-            const uint64_t tk = warp_prune(reinterpret_cast<uint64_t*>(bptr), bcnt, p.kc, hist, lane);
-            if (lane == src) {
-              cnt = p.kc;
-              thr = key_sim(tk);
+          if (active) {
+            float* dst = p.cmax + q * static_cast<int64_t>(p.num_chunks);
+            const int per8 = p.chunk_w >> 3;          // 1, 2 or 4 groups of 8 per chunk
+            const int nch = kBlockN / p.chunk_w;      // chunks per tile
+            const int c0 = static_cast<int>(gbase / p.chunk_w);
+            if (per8 == 1) {
+#pragma unroll
+              for (int i = 0; i < kBlockN / 8; ++i)
+                if (c0 + i < p.num_chunks) dst[c0 + i] = m8[i];
+            } else if (per8 == 2) {
+#pragma unroll
+              for (int i = 0; i < kBlockN / 16; ++i)
+                if (c0 + i < p.num_chunks) dst[c0 + i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < kBlockN / 32; ++i)
+                if (c0 + i < p.num_chunks)
+                  dst[c0 + i] = fmaxf(fmaxf(m8[4 * i], m8[4 * i + 1]), fmaxf(m8[4 * i + 2], m8[4 * i + 3]));
             }
+            (void)nch;
           }
         }
       }
-      // end of work item: leave at most kc candidates per list, publish the count
-      uint32_t need = __ballot_sync(kFull, cnt > p.kc);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const uint64_t bptr = __shfl_sync(kFull, reinterpret_cast<uint64_t>(buf), src);
-        const int bcnt = __shfl_sync(kFull, cnt, src);
-        warp_prune(reinterpret_cast<uint64_t*>(bptr), bcnt, p.kc, hist, lane);
-        if (lane == src) cnt = p.kc;
+    } else {
+      // ---- main pass: TMEM -> threshold filter -> candidate lists ----
+      constexpr bool kDump = (kMode == kModeDump);
+      uint32_t* hist = hist_all + ew * 256;
+      const int prune_at = p.cap - 32;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int split = item / p.num_qt, qt = item - split * p.num_qt;
+        const int t0 = split * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        const int64_t q = static_cast<int64_t>(qt) * kBlockM + row;
+        const bool active = q < p.nq;
+        float thr = INFINITY;  // inactive rows (and the benchmark-only 'emit nothing' flag) pass nothing
+        if (active && !(p.flags & HCIR_FLAG_NO_EMIT)) thr = p.thr0 ? p.thr0[q] : -INFINITY;
+        int cnt = 0;
+        uint64_t* buf = p.keys + (active ? (q * p.nsplit + split) * static_cast<int64_t>(p.cap) : 0);
+        for (int t = t0; t < t1; ++t, ++iter) {
+          const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
+          ptx::mbar_wait(&tfull_bar[acc], aphase);
+          ptx::tc_fence_after();
+          const int64_t gbase = static_cast<int64_t>(t) * kBlockN;
+          const bool full_tile = gbase + kBlockN <= p.ng;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN;
+#pragma unroll 1
+          for (int c = 0; c < kBlockN / 32; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            if (c == kBlockN / 32 - 1) {
+              // whole accumulator stage is in registers now: hand it back to the MMA warp
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            }
+            const uint32_t gcol0 = static_cast<uint32_t>(gbase) + c * 32;
+            if (full_tile) {
+              scan_chunk<false>(v, thr, buf, cnt, gcol0, 32);
+            } else {
+              const int64_t rem = p.ng - static_cast<int64_t>(gcol0);
+              const int lim = rem >= 32 ? 32 : (rem > 0 ? static_cast<int>(rem) : 0);
+              scan_chunk<true>(v, thr, buf, cnt, gcol0, lim);
+            }
+            if (kDump && active) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t g = static_cast<int64_t>(gcol0) + j;
+                if (g < p.ng) p.dump[q * p.ng + g] = __uint_as_float(v[j]);
+              }
+            }
+            // lists that could overflow during the next chunk are pruned back to kc now (rare:
+            // the sample-pass threshold keeps the expected list length well below cap)
+            uint32_t need = __ballot_sync(kFull, cnt > prune_at);
+            while (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              const uint64_t bptr = __shfl_sync(kFull, reinterpret_cast<uint64_t>(buf), src);
+              const int bcnt = __shfl_sync(kFull, cnt, src);
+              const uint64_t tk = warp_prune<true>(reinterpret_cast<uint64_t*>(bptr), bcnt, p.kc, hist, lane);
+              if (lane == src) {
+                cnt = p.kc;
+                thr = key_sim(tk);
+              }
+            }
+          }
+        }
+        if (active) {
+          p.counts[q * p.nsplit + split] = cnt;
+          p.thr_out[q * p.nsplit + split] = thr;
+        }
       }
-      if (active) p.counts[q * p.nsplit + split] = cnt;
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// threshold kernel: thr0[q] = kc-th largest chunk maximum of the sample pass.  Every chunk
+// maximum is the score of a distinct real gallery row, so at least kc rows score >= thr0[q]:
+// the main pass may drop everything <= thr0[q] without losing a top-kc candidate.
+// grid nq, block 128, dynamic smem: num_chunks keys + hist + scratch.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+threshold_kernel(const float* __restrict__ cmax, int num_chunks, int kc, float* __restrict__ thr0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(keys + num_chunks);
+  uint32_t* scratch = hist + 256;
+  const int64_t q = blockIdx.x;
+  const float* src = cmax + q * static_cast<int64_t>(num_chunks);
+  for (int i = threadIdx.x; i < num_chunks; i += blockDim.x) keys[i] = make_key(src[i], static_cast<uint32_t>(i));
+  __syncthreads();
+  if (num_chunks < kc) {
+    if (threadIdx.x == 0) thr0[q] = -INFINITY;
+    return;
+  }
+  const uint64_t t = block_select(keys, num_chunks, kc, nullptr, hist, scratch);
+  if (threadIdx.x == 0) thr0[q] = key_sim(t);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,25 +370,57 @@ static PFN_tensorMapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-// [rows, ld] bf16 row-major -> 2D tensor map, box = 64 x box_rows, 128-byte swizzle, zero OOB fill
-static int make_bf16_map(CUtensorMap* map, const void* base, int64_t rows, int ld, int box_rows) {
+// rows x ld bf16 (row r at base + r*row_stride elements) -> 2D tensor map, box = 64 x box_rows,
+// 128-byte swizzle, zero OOB fill.  row_stride > ld describes a strided row sample in place.
+static int make_bf16_map(CUtensorMap* map, const void* base, int64_t rows, int ld, int64_t row_stride,
+                         int box_rows) {
   PFN_tensorMapEncodeTiled enc = get_encode_fn();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return HCIR_ECUDA;
   }
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(row_stride) * 2};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%d box_rows=%d base=%p)",
-              static_cast<int>(r), (long long)rows, ld, box_rows, base);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%d stride=%lld box_rows=%d base=%p)",
+              static_cast<int>(r), (long long)rows, ld, (long long)row_stride, box_rows, base);
     return HCIR_ECUDA;
   }
+  return HCIR_OK;
+}
+
+// balanced split count for `tiles` gallery tiles x `num_qt` query tiles over persistent CTAs:
+// static round-robin => time ~ waves * tiles-per-item
+static int balanced_nsplit(int64_t num_qt, int64_t tiles, int64_t max_split, int sm_count) {
+  if (max_split > tiles) max_split = tiles;
+  if (max_split < 1) max_split = 1;
+  double best_cost = 1e300;
+  int best = 1;
+  for (int64_t ns = 1; ns <= max_split; ++ns) {
+    const int64_t tps = ceil_div_i64(tiles, ns);
+    if (ceil_div_i64(tiles, tps) != ns) continue;
+    const int64_t waves = ceil_div_i64(num_qt * ns, sm_count);
+    const double cost = static_cast<double>(waves) * (static_cast<double>(tps) + 0.5);
+    if (cost < best_cost * 0.995) {
+      best_cost = cost;
+      best = static_cast<int>(ns);
+    }
+  }
+  return best;
+}
+
+template <int kMode>
+static int launch_mode(const CUtensorMap& mq, const CUtensorMap& mg, const SimParams& p, int sms, cudaStream_t st) {
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  HCIR_CUDA_TRY(cudaFuncSetAttribute(simtopk_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(kSimSmemBytes)));
+  simtopk_kernel<kMode><<<grid, kSimThreads, kSimSmemBytes, st>>>(mq, mg, p);
+  HCIR_CUDA_TRY(cudaGetLastError());
   return HCIR_OK;
 }
 
@@ -299,46 +436,77 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
   HCIR_REQUIRE(plan->kc > 0 && plan->cap >= plan->kc + 64 && plan->nsplit > 0, "simtopk: inconsistent plan");
   int rc = check_device();
   if (rc != HCIR_OK) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  char* ws = static_cast<char*>(workspace);
 
-  SimParams p;
+  CUtensorMap mq, mg;
+  rc = make_bf16_map(&mq, q_bf16, nq, ld, ld, kBlockM);
+  if (rc != HCIR_OK) return rc;
+
+  SimParams p{};
   p.nq = nq;
-  p.ng = ng;
   p.ld = ld;
   p.num_kb = ld / kBlockK;
   p.num_qt = static_cast<int>(ceil_div_i64(nq, kBlockM));
+  p.kc = plan->kc;
+  float* thr0 = nullptr;
+
+  // ---- sample pass + thresholds -------------------------------------------------------------
+  const bool run_sample = !(plan->flags & HCIR_FLAG_MAIN_ONLY);
+  const bool run_main = !(plan->flags & HCIR_FLAG_SAMPLE_ONLY);
+  if (plan->sample_rows > 0 && !run_sample) thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
+  if (plan->sample_rows > 0 && run_sample) {
+    HCIR_REQUIRE(plan->chunk_w == 8 || plan->chunk_w == 16 || plan->chunk_w == 32, "simtopk: bad chunk_w=%d",
+                 plan->chunk_w);
+    HCIR_REQUIRE(plan->sample_stride >= 1 &&
+                     static_cast<int64_t>(plan->sample_rows - 1) * plan->sample_stride < ng,
+                 "simtopk: sample (%d rows, stride %d) exceeds the gallery", plan->sample_rows, plan->sample_stride);
+    CUtensorMap ms;
+    rc = make_bf16_map(&ms, g_bf16, plan->sample_rows, ld, static_cast<int64_t>(plan->sample_stride) * ld, kBlockN);
+    if (rc != HCIR_OK) return rc;
+    SimParams sp = p;
+    sp.ng = plan->sample_rows;
+    sp.tiles_total = static_cast<int>(ceil_div_i64(sp.ng, kBlockN));
+    sp.nsplit = plan->sample_nsplit;
+    sp.tiles_per_split = static_cast<int>(ceil_div_i64(sp.tiles_total, sp.nsplit));
+    HCIR_REQUIRE(static_cast<int>(ceil_div_i64(sp.tiles_total, sp.tiles_per_split)) == sp.nsplit,
+                 "simtopk: plan.sample_nsplit=%d leaves an empty split", sp.nsplit);
+    sp.num_items = sp.num_qt * sp.nsplit;
+    sp.cmax = reinterpret_cast<float*>(ws + plan->cmax_off);
+    sp.chunk_w = plan->chunk_w;
+    sp.num_chunks = plan->num_chunks;
+    rc = launch_mode<kModeSample>(mq, ms, sp, sms, st);
+    if (rc != HCIR_OK) return rc;
+    thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
+    const size_t smem = static_cast<size_t>(plan->num_chunks) * 8 + (256 + 8) * 4;
+    HCIR_REQUIRE(smem <= 200 * 1024, "simtopk: %d sample chunks do not fit in shared memory", plan->num_chunks);
+    HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    threshold_kernel<<<static_cast<unsigned>(nq), 128, smem, st>>>(sp.cmax, plan->num_chunks, plan->kc, thr0);
+    HCIR_CUDA_TRY(cudaGetLastError());
+  }
+
+  // ---- main pass ----------------------------------------------------------------------------
+  if (!run_main) return HCIR_OK;
+  rc = make_bf16_map(&mg, g_bf16, ng, ld, ld, kBlockN);
+  if (rc != HCIR_OK) return rc;
+  p.ng = ng;
   p.tiles_total = static_cast<int>(ceil_div_i64(ng, kBlockN));
   p.tiles_per_split = static_cast<int>(ceil_div_i64(p.tiles_total, plan->nsplit));
   HCIR_REQUIRE(static_cast<int>(ceil_div_i64(p.tiles_total, p.tiles_per_split)) == plan->nsplit,
                "simtopk: plan.nsplit=%d leaves an empty split for %d tiles", plan->nsplit, p.tiles_total);
   p.nsplit = plan->nsplit;
   p.cap = plan->cap;
-  p.kc = plan->kc;
   p.num_items = p.num_qt * p.nsplit;
-  p.counts = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + plan->counts_off);
-  p.keys = reinterpret_cast<uint64_t*>(static_cast<char*>(workspace) + plan->keys_off);
+  p.counts = reinterpret_cast<int32_t*>(ws + plan->counts_off);
+  p.keys = reinterpret_cast<uint64_t*>(ws + plan->keys_off);
+  p.thr0 = thr0;
+  p.thr_out = reinterpret_cast<float*>(ws + plan->thr_out_off);
   p.dump = dump;
-
-  CUtensorMap mq, mg;
-  rc = make_bf16_map(&mq, q_bf16, nq, ld, kBlockM);
-  if (rc != HCIR_OK) return rc;
-  rc = make_bf16_map(&mg, g_bf16, ng, ld, kBlockN);
-  if (rc != HCIR_OK) return rc;
-
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.num_items < sms ? p.num_items : sms;
-  if (dump != nullptr) {
-    HCIR_CUDA_TRY(cudaFuncSetAttribute(simtopk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kSimSmemBytes)));
-    simtopk_kernel<true><<<grid, kSimThreads, kSimSmemBytes, st>>>(mq, mg, p);
-  } else {
-    HCIR_CUDA_TRY(cudaFuncSetAttribute(simtopk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kSimSmemBytes)));
-    simtopk_kernel<false><<<grid, kSimThreads, kSimSmemBytes, st>>>(mq, mg, p);
-  }
-  HCIR_CUDA_TRY(cudaGetLastError());
-  return HCIR_OK;
+  p.flags = plan->flags;
+  return dump != nullptr ? launch_mode<kModeDump>(mq, mg, p, sms, st) : launch_mode<kModeMain>(mq, mg, p, sms, st);
 }
 
 }  // namespace hcir
@@ -351,35 +519,52 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   if (sm_count <= 0) sm_count = 148;
   const int64_t num_qt = ceil_div_i64(nq, kBlockM);
   const int64_t tiles = ceil_div_i64(ng, kBlockN);
-  int64_t max_split = tiles;
-  if (max_split > 16384 / kc) max_split = 16384 / kc;  // select_rescore keeps nsplit*kc keys in smem
-  if (max_split > 4 * sm_count) max_split = 4 * sm_count;
-  if (max_split < 1) max_split = 1;
-  // static round-robin over persistent CTAs: time ~ waves * (tiles per item + list warm-up)
-  const double warmup_tiles = 16.0;
-  double best_cost = 1e300;
-  int best = 1;
-  for (int64_t ns = 1; ns <= max_split; ++ns) {
-    const int64_t tps = ceil_div_i64(tiles, ns);
-    const int64_t ns_eff = ceil_div_i64(tiles, tps);
-    if (ns_eff != ns) continue;
-    const int64_t items = num_qt * ns_eff;
-    const int64_t waves = ceil_div_i64(items, sm_count);
-    const double cost = static_cast<double>(waves) * (static_cast<double>(tps) + warmup_tiles);
-    if (cost < best_cost * 0.995) {
-      best_cost = cost;
-      best = static_cast<int>(ns);
-    }
-  }
-  plan->nsplit = best;
+  *plan = hcir_plan_t{};
   plan->kc = kc;
-  plan->cap = round_up_int(2 * kc + 32, 32);
-  plan->reserved = 0;
-  plan->counts_off = 0;
-  uint64_t off = static_cast<uint64_t>(nq) * best * sizeof(int32_t);
-  off = (off + 255) / 256 * 256;
-  plan->keys_off = off;
-  plan->bytes = off + static_cast<uint64_t>(nq) * best * plan->cap * sizeof(uint64_t);
+  plan->nsplit = balanced_nsplit(num_qt, tiles, 4 * sm_count, sm_count);
+
+  // sample pass: num_chunks = 2*kc chunk maxima over S = 2*kc*chunk_w strided gallery rows, as long
+  // as the sample stays a small fraction of the gallery (its contraction is extra work)
+  int64_t S = 0;
+  int w = 0;
+  if (64ll * kc * 16 <= ng) { w = 32; S = 64ll * kc; }
+  else if (32ll * kc * 12 <= ng) { w = 16; S = 32ll * kc; }
+  else if (16ll * kc * 4 <= ng) { w = 8; S = 16ll * kc; }
+  double pass_rate = 1.0;
+  if (S > 0) {
+    S = (S + kBlockN - 1) / kBlockN * kBlockN;  // whole tiles
+    plan->sample_rows = static_cast<int32_t>(S);
+    plan->sample_stride = static_cast<int32_t>(ng / S);
+    plan->chunk_w = w;
+    plan->num_chunks = static_cast<int32_t>(S / w);
+    plan->sample_nsplit = balanced_nsplit(num_qt, S / kBlockN, 4 * sm_count, sm_count);
+    // kc-th best of m chunk maxima ~ the (-m ln(1 - kc/m))-th best sample row
+    const double m = static_cast<double>(plan->num_chunks);
+    pass_rate = -m * log(1.0 - kc / m) / static_cast<double>(S);
+  }
+  // list capacity: expected appends per (query, split) list with head-room, bounded so that the
+  // prune path (not the workspace) absorbs adversarial data
+  const int64_t tps = ceil_div_i64(tiles, plan->nsplit);
+  const double mu = pass_rate * static_cast<double>(tps * kBlockN);
+  int64_t cap = 2 * kc + 32;
+  if (S > 0) {
+    const int64_t want = static_cast<int64_t>(1.5 * mu) + 96;
+    const int64_t hi = 8ll * kc;
+    cap = want < cap ? cap : (want > hi ? hi : want);
+  }
+  plan->cap = round_up_int(static_cast<int>(cap), 32);
+  uint64_t off = 0;
+  auto take = [&off](uint64_t bytes) {
+    const uint64_t at = off;
+    off = (off + bytes + 255) / 256 * 256;
+    return at;
+  };
+  plan->counts_off = take(static_cast<uint64_t>(nq) * plan->nsplit * sizeof(int32_t));
+  plan->thr_out_off = take(static_cast<uint64_t>(nq) * plan->nsplit * sizeof(float));
+  plan->thr0_off = take(static_cast<uint64_t>(nq) * sizeof(float));
+  plan->cmax_off = take(static_cast<uint64_t>(nq) * plan->num_chunks * sizeof(float));
+  plan->keys_off = take(static_cast<uint64_t>(nq) * plan->nsplit * plan->cap * sizeof(uint64_t));
+  plan->bytes = off;
   return HCIR_OK;
 }
 

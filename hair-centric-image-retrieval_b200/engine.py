@@ -219,8 +219,18 @@ class GalleryBank:
         plan = Plan()
         _lib.check(lib.hcir_simtopk_plan(nq, self.n, self.ld, kc, self.sm_count, plan), "simtopk_plan")
         ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
-        _lib.check(self._timed("simtopk", lambda: lib.hcir_simtopk(
-            qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan, ws.data_ptr(), st)), "simtopk")
+        if self.kernel_events is not None and plan.sample_rows > 0:
+            # measurement only: enqueue the two phases separately so each gets its own events
+            for name, flag, nk in (("simtopk_sample", 2, 2), ("simtopk", 4, 1)):
+                plan.flags = flag
+                _lib.check(self._timed(name, lambda: lib.hcir_simtopk(
+                    qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan, ws.data_ptr(), st),
+                    n_kernels=nk), name)
+            plan.flags = 0
+        else:
+            _lib.check(self._timed("simtopk", lambda: lib.hcir_simtopk(
+                qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan, ws.data_ptr(), st),
+                n_kernels=plan.kernels()), "simtopk")
         unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
         unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
         _lib.check(self._timed("select_rescore", lambda: lib.hcir_select_rescore(
@@ -231,7 +241,8 @@ class GalleryBank:
         if n_unc > 0:
             self._exact(q32, unc_list, n_unc, k, out_sim, out_idx)
         self.last_stats = {"path": "tensor", "uncertified": n_unc, "nsplit": int(plan.nsplit),
-                           "kc": int(plan.kc), "cap": int(plan.cap), "workspace_bytes": int(plan.bytes)}
+                           "kc": int(plan.kc), "cap": int(plan.cap), "workspace_bytes": int(plan.bytes),
+                           "sample_rows": int(plan.sample_rows), "chunk_w": int(plan.chunk_w)}
         return out_sim, out_idx
 
     def _exact(self, q32, qlist, nlist, k, out_sim, out_idx):

@@ -35,7 +35,12 @@ extern "C" {
 #define HCIR_ECUDA (-3)      /* a CUDA runtime / driver call failed                        */
 #define HCIR_EWORKSPACE (-4) /* workspace too small                                        */
 
-#define HCIR_ABI_VERSION 1
+#define HCIR_ABI_VERSION 2
+
+/* hcir_plan_t.flags: measurement aids, all 0 in production */
+#define HCIR_FLAG_NO_EMIT 1     /* main pass emits nothing: pure contraction throughput        */
+#define HCIR_FLAG_SAMPLE_ONLY 2 /* enqueue only the sample pass + threshold kernel             */
+#define HCIR_FLAG_MAIN_ONLY 4   /* enqueue only the main pass (thr0 already in the workspace)  */
 
 typedef void* hcir_stream_t; /* cudaStream_t */
 
@@ -59,25 +64,42 @@ int hcir_padded_dim(int d);
 int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, float* out_f32,
                      uint16_t* out_bf16, int ld, float* out_delta, hcir_stream_t stream);
 
-/* K2 -- similarity contraction fused with a running top-kc.  Replaces
+/* K2 -- similarity contraction fused with the top-kc candidate filter.  Replaces
  * torch.mm(q, G.t()) (qualitative_test.py:79, dual_view_model.py:333), the sgemm inside
  * sklearn's pairwise cosine (classification_engine.py:82; hair_encoder.py:193) and faiss
  * IndexFlatL2.search (inference.py:108) together with the N-wide partial sort that follows
  * them.  bf16 x bf16 -> fp32 on tcgen05 tensor cores (TMA-fed, accumulators in TMEM); the
- * [nq, ng] similarity matrix is never written to memory.  Output: for every query and
- * every gallery split a list of at most `kc` candidate KEYS (bf16-contraction scores) such
- * that every gallery row NOT listed scores <= the kc-th best listed score of that query.
+ * [nq, ng] similarity matrix is never written to memory.  One call enqueues up to three
+ * kernels:
+ *   1. sample pass   the same contraction over a strided sample of `sample_rows` gallery rows
+ *                    (addressed in place through the TMA row stride); the epilogue keeps only
+ *                    the maximum of every `chunk_w` consecutive sample columns;
+ *   2. thresholds    thr0[q] = kc-th largest chunk maximum: >= kc real gallery rows score
+ *                    >= thr0[q], so nothing <= thr0[q] can be a top-kc candidate;
+ *   3. main pass     full contraction; the epilogue compares every accumulator value with the
+ *                    query's threshold and appends the survivors (64-bit keys) to one list per
+ *                    (query, gallery split).  A list that fills up is pruned back to its kc
+ *                    best in place and its threshold raised (rare).
+ * Output: for every query and split a list of at most `cap` candidate KEYS (bf16-contraction
+ * scores) and the threshold the list ended with, such that every gallery row of that split
+ * NOT listed scores <= that threshold.
  *
- * hcir_simtopk_plan fills the launch plan: number of gallery splits, list capacity and the
- * workspace size.  Workspace layout: int32 counts[nq][nsplit]; uint64 keys[nq][nsplit][cap]. */
+ * hcir_simtopk_plan fills the launch plan and the workspace layout (all offsets in bytes):
+ *   int32 counts[nq][nsplit]; float thr_out[nq][nsplit]; float thr0[nq];
+ *   float cmax[nq][num_chunks]; uint64 keys[nq][nsplit][cap]. */
 typedef struct {
-  int32_t nsplit;      /* gallery splits (one candidate list per query per split)       */
-  int32_t cap;         /* capacity of one candidate list (>= kc + 64)                   */
-  int32_t kc;          /* candidates kept per list                                      */
+  int32_t nsplit;        /* gallery splits of the main pass (one list per query per split) */
+  int32_t cap;           /* capacity of one candidate list (>= kc + 64)                    */
+  int32_t kc;            /* candidates that must survive per query                         */
+  int32_t flags;         /* HCIR_FLAG_* (0 in production)                                  */
+  int32_t sample_rows;   /* rows of the strided sample; 0 = no sample pass (thr0 = -inf)   */
+  int32_t sample_stride; /* sample row i = gallery row i * sample_stride                   */
+  int32_t chunk_w;       /* 8, 16 or 32 sample columns per chunk maximum                   */
+  int32_t num_chunks;    /* sample_rows / chunk_w                                          */
+  int32_t sample_nsplit; /* splits of the sample pass                                      */
   int32_t reserved;
-  uint64_t counts_off; /* byte offset of counts[] in the workspace                      */
-  uint64_t keys_off;   /* byte offset of keys[] in the workspace                        */
-  uint64_t bytes;      /* total workspace bytes                                         */
+  uint64_t counts_off, thr_out_off, thr0_off, cmax_off, keys_off;
+  uint64_t bytes;        /* total workspace bytes                                          */
 } hcir_plan_t;
 
 int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_count, hcir_plan_t* plan);
@@ -92,11 +114,12 @@ int hcir_simtopk_debug(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf1
 /* K3 -- candidate selection + fp32 re-score + exact sort + certification.  Replaces
  * torch.topk(sim, k) (qualitative_test.py:82), np.argsort(s)[::-1][:k]
  * (hair_encoder.py:194) and sklearn's argpartition+argsort (_kneighbors_reduce_func).
- * Per query: merge the split lists, keep the kc best by bf16 score, re-score with the
+ * Per query: stream the split lists, keep the kc best by bf16 score, re-score with the
  * canonical fp32 dot product only the candidates that can still reach the top-k, emit the
  * exact top-k in canonical order, and certify it:
  *     certified <=> (all gallery rows were candidates) or
- *                   fp32_score(k-th) > bf16_score(kc-th) + eps(query)
+ *                   fp32_score(k-th) > t' + eps(query),
+ *     t' = max(bf16_score(kc-th best candidate), largest list threshold)
  *     eps = g_delta_max*(1+q_delta) + q_delta*(1+1e-6) + eps_acc
  * Uncertified queries are appended to uncert_list / *uncert_count for hcir_exact_topk.
  *   out_sim [nq,k] fp32 descending, out_idx [nq,k] int64 (= local row + idx_offset). */

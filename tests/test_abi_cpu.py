@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_builds_and_loads():
     lib = _lib.load()
     assert os.path.exists(_build.LIB_PATH)
-    assert lib.hcir_abi_version() == 1
+    assert lib.hcir_abi_version() == 2
     assert lib.hcir_padded_dim(768) == 768 and lib.hcir_padded_dim(512) == 512
     assert lib.hcir_padded_dim(100) == 128 and lib.hcir_padded_dim(2048) == 2048
 
@@ -55,9 +55,17 @@ def test_plan_is_consistent():
         tiles = -(-ng // 256)
         tps = -(-tiles // p.nsplit)
         assert -(-tiles // tps) == p.nsplit, "empty split"
-        assert p.cap >= p.kc + 64 and p.cap % 32 == 0
-        assert p.nsplit * p.kc <= 16384 or p.nsplit == 1
+        assert p.cap >= p.kc + 64 and p.cap % 32 == 0 and p.cap <= max(2 * p.kc + 64, 8 * p.kc)
         assert p.bytes >= p.keys_off + nq * p.nsplit * p.cap * 8
+        assert p.keys_off % 256 == 0 and p.cmax_off % 256 == 0
+        if p.sample_rows:
+            assert p.sample_rows % 256 == 0 and p.chunk_w in (8, 16, 32)
+            assert p.num_chunks * p.chunk_w == p.sample_rows and p.num_chunks >= 2 * p.kc
+            assert (p.sample_rows - 1) * p.sample_stride < ng and p.sample_rows * 4 <= ng + 1024
+            st = -(-(p.sample_rows // 256) // p.sample_nsplit)
+            assert -(-(p.sample_rows // 256) // st) == p.sample_nsplit
+        else:
+            assert ng < 64 * p.kc
     assert lib.hcir_simtopk_plan(0, 10, 64, 10, 148, p) == _lib.HCIR_EINVAL
     assert "bad shape" in _lib.last_error()
 
