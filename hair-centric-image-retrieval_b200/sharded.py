@@ -46,14 +46,16 @@ def exchange_candidates(sims: torch.Tensor, idx: torch.Tensor, labels: torch.Ten
     """The path's single collective: all-gather every rank's [Q, k] exact local top-k
     (fp32 sims, int64 global indices, optional int32 labels) -> [G, Q, k] on every rank."""
     world = dist.get_world_size(group)
-    g_sims = torch.empty((world,) + tuple(sims.shape), dtype=sims.dtype, device=sims.device)
-    g_idx = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(g_sims, sims.contiguous(), group=group)
-    dist.all_gather_into_tensor(g_idx, idx.contiguous(), group=group)
-    g_lab = None
-    if labels is not None:
-        g_lab = torch.empty((world,) + tuple(labels.shape), dtype=labels.dtype, device=labels.device)
-        dist.all_gather_into_tensor(g_lab, labels.contiguous(), group=group)
+
+    def gather(t: torch.Tensor) -> torch.Tensor:
+        t = t.contiguous()
+        # concatenated-along-dim-0 output: the one layout both NCCL and gloo accept
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.view((world,) + tuple(t.shape))
+
+    g_sims, g_idx = gather(sims), gather(idx)
+    g_lab = gather(labels) if labels is not None else None
     return g_sims, g_idx, g_lab
 
 
