@@ -309,7 +309,7 @@ extern "C" int hcir_select_rescore(const float* q_f32, const float* g_f32, int l
   int rc = check_device();
   if (rc != HCIR_OK) return rc;
   if (nq == 0) return HCIR_OK;
-  const SelSmem L = sel_smem_layout(plan->nsplit, plan->kc, ld);
+  const SelSmem L = sel_smem_layout(plan->nlists, plan->kc, ld);
   HCIR_REQUIRE(L.total <= 220 * 1024, "select_rescore: kc=%d ld=%d needs %zu B of shared memory", plan->kc, ld,
                L.total);
   HCIR_CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -319,7 +319,7 @@ extern "C" int hcir_select_rescore(const float* q_f32, const float* g_f32, int l
   const uint64_t* cand = reinterpret_cast<const uint64_t*>(ws + plan->keys_off);
   const float* thr_out = reinterpret_cast<const float*>(ws + plan->thr_out_off);
   select_rescore_kernel<<<static_cast<unsigned>(nq), kSelThreads, L.total, static_cast<cudaStream_t>(stream)>>>(
-      q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nsplit, plan->cap, plan->kc, counts, cand, thr_out, q_delta,
+      q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, q_delta,
       g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
   HCIR_CUDA_TRY(cudaGetLastError());
   return HCIR_OK;

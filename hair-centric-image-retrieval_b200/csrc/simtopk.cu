@@ -9,13 +9,15 @@
 // (ng*ld*2 gallery bytes streamed once).  See DESIGN.md for the numbers.
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over work items):
-//   warp 0    TMA producer     (one lane)   global -> 4-stage smem ring, SWIZZLE_128B
-//   warp 1    MMA issuer       (one lane)   tcgen05.mma 128x256x16, 2 TMEM accumulator stages
-//   warp 2    TMEM allocator
-//   warps 4-7 epilogue         (128 threads = 128 TMEM lanes = 128 query rows)
+//   warps 0-3 epilogue         (128 threads = 128 TMEM lanes = 128 query rows)
+//   warp 4    TMA producer     (one lane)   global -> 4-stage smem ring, SWIZZLE_128B
+//   warp 5    MMA issuer       (one lane)   tcgen05.mma 128x256x16, 2 TMEM accumulator stages
+//   warp 6    TMEM allocator   (warp 7 idle)
 // Work item = (query tile of 128 rows) x (gallery split = contiguous range of 256-row tiles).
 #include <cuda.h>
 #include <math.h>
+
+#include <utility>
 
 #include "hcir_common.cuh"
 #include "hcir_ptx.cuh"
@@ -31,19 +33,31 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kBBytes = kBlockN * kBlockK * 2;  // 32 KiB
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBlockN;  // 512: all of TMEM
-constexpr int kSimThreads = 256;
-constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 4;
+// Epilogue warps 0 .. 4*kColHalves-1: warp % 4 = TMEM lane quarter (32 query rows), warp / 4 =
+// column slice of the tile.  Measured: the epilogue is bound by the half-rate ALU pipe, not by
+// warp count, so one warp per scheduler (kColHalves = 1) is as fast as two and needs half the
+// staging memory.
+constexpr int kColHalves = 1;
+constexpr int kNumEpiWarps = 4 * kColHalves;
+constexpr int kHalfCols = kBlockN / kColHalves;
+constexpr int kTmaWarp = kNumEpiWarps;        // single-thread roles on the highest warp ids
+constexpr int kMmaWarp = kNumEpiWarps + 1;
+constexpr int kAllocWarp = kNumEpiWarps + 2;
+constexpr int kSimThreads = (kNumEpiWarps + 4) * 32;
+// per-warp staging of one chunk's survivor values: [32 columns][32 lanes] x 4 bytes (column-major:
+// conflict-free for any set of active lanes); doubles as the prune scratch
+constexpr int kStageBytesPerWarp = 32 * 32 * 4;
 constexpr size_t kSimSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kStages) * (kABytes + kBBytes) +
-                                 256 /*barriers + tmem slot*/ + kNumEpiWarps * 256 * sizeof(uint32_t);
+                                 256 /*barriers + tmem slot*/ + kNumEpiWarps * kStageBytesPerWarp;
 
 struct SimParams {
   int64_t nq, ng;
   int ld, num_kb, num_qt, tiles_total, tiles_per_split, nsplit, cap, kc, num_items, flags;
-  int32_t* counts;    // [nq][nsplit]      main: candidates per list
-  uint64_t* keys;     // [nq][nsplit][cap] main: candidate keys
+  // one candidate list per (query, gallery split, column half): nlists = kColHalves * nsplit
+  int32_t* counts;    // [nq][nlists]      main: candidates per list
+  uint64_t* keys;     // [nq][nlists][cap] main: candidate keys (RAW, see scan_chunk)
   const float* thr0;  // [nq] or null      main: initial per-query threshold (from the sample pass)
-  float* thr_out;     // [nq][nsplit]      main: threshold each list ended with
+  float* thr_out;     // [nq][nlists]      main: threshold each list ended with
   float* dump;        // [nq][ng]          debug: raw accumulator values
   float* cmax;        // [nq][num_chunks]  sample: maxima of `chunk_w` consecutive sample columns
   int chunk_w, num_chunks;
@@ -51,40 +65,55 @@ struct SimParams {
 
 enum : int { kModeMain = 0, kModeDump = 1, kModeSample = 2 };
 
+// column J of the chunk: compare, predicated store into staging slot J, predicated mask bit
+template <bool kBounded, int J>
+__device__ __forceinline__ void scan_column(uint32_t bits, float thr, int lim, uint32_t stage_lane, uint32_t& m) {
+  const uint32_t hit = ((__uint_as_float(bits) > thr) && (!kBounded || J < lim)) ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "@p st.shared.b32 [%2+%3], %4;\n\t"
+      "@p or.b32 %0, %0, %5;\n\t"
+      "}"
+      : "+r"(m)
+      : "r"(hit), "r"(stage_lane), "n"(J * 128), "r"(bits), "n"(1u << J)
+      : "memory");
+}
+template <bool kBounded, int... Js>
+__device__ __forceinline__ void scan_columns(const uint32_t (&v)[32], float thr, int lim, uint32_t stage_lane,
+                                             uint32_t& m, std::integer_sequence<int, Js...>) {
+  (scan_column<kBounded, Js>(v[Js], thr, lim, stage_lane, m), ...);
+}
+
 // Scan one 32-column chunk of accumulator values: lane = query row, v[j] = column gcol0 + j.
 // Survivors (value > the row's threshold) are appended to the row's list as RAW keys
 // (fp32 bits << 32 | ~index; consumers apply the order-preserving transform on load).
-// The epilogue warp is alone on its scheduler, so what matters is the dependent-instruction
-// chain, not the instruction count: after one warp-wide vote that skips chunks without any
-// survivor, the code is branch-free -- 32 independent compare / predicated-store groups whose
-// only serial dependency is the list cursor.
+// The epilogue is bound by instruction issue on the half-rate ALU pipe and by scoreboard
+// round trips through the shared-memory unit, so the per-column code is three independent
+// instructions with no address arithmetic: compare, predicated 4-byte store of the value into
+// slot j of this lane's staging column (immediate offset), predicated OR into a hit mask.
+// The few survivors are then read back by dynamic slot index (shared memory can be indexed,
+// registers cannot) and copied to the list in global memory.
 template <bool kBounded>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, uint64_t* buf, int& cnt,
-                                           uint32_t gcol0, int lim) {
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float f = __uint_as_float(v[j]);
-    mx = fmaxf(mx, (kBounded && j >= lim) ? -INFINITY : f);
-  }
-  if (!__any_sync(kFull, mx > thr)) return;
-  uint64_t* dst = buf + cnt;
+                                           uint32_t gcol0, int lim, uint32_t stage_lane) {
+  uint32_t m = 0;
+  scan_columns<kBounded>(v, thr, lim, stage_lane, m, std::make_integer_sequence<int, 32>{});
+  if (!__any_sync(kFull, m != 0u)) return;
   const uint32_t inv0 = 0xFFFFFFFFu - gcol0;
-  int c = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const uint32_t hit = ((__uint_as_float(v[j]) > thr) && (!kBounded || j < lim)) ? 1u : 0u;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.u32 p, %0, 0;\n\t"
-        "@p st.global.v2.b32 [%1], {%2, %3};\n\t"
-        "}" ::"r"(hit),
-        "l"(dst + c), "r"(inv0 - j), "r"(v[j])
-        : "memory");
-    c += hit;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(buf + cnt);
+  cnt += __popc(m);
+  while (m != 0u) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1u;
+    uint32_t bits;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bits) : "r"(stage_lane + static_cast<uint32_t>(j) * 128u) : "memory");
+    asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(inv0 - static_cast<uint32_t>(j)), "r"(bits)
+                 : "memory");
+    dst += 2;
   }
-  cnt += c;
+  __syncwarp();
 }
 
 template <int kMode>
@@ -102,15 +131,15 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * kStages;           // [kAccStages] MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kStages + kAccStages;  // [kAccStages] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
-  uint32_t* hist_all = reinterpret_cast<uint32_t*>(smem + kStages * (kABytes + kBBytes) + 256);
+  uint8_t* stage_all = smem + kStages * (kABytes + kBBytes) + 256;  // kNumEpiWarps x kStageBytesPerWarp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_g);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -121,13 +150,13 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
+  if (warp == kAllocWarp) ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -149,7 +178,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, kBlockN);
@@ -182,11 +211,13 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
       }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp < kNumEpiWarps) {
     // ===================== epilogue =====================
-    const int ew = warp - kEpiWarp0;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = warp & 3;    // TMEM lane quarter this warp may read (hardware rule: warp % 4)
+    const int half = warp >> 2;  // column half of every tile this warp scans
     const int row = ew * 32 + lane;
     uint32_t iter = 0;
+    constexpr int kChunks = kHalfCols / 32;  // 32-column chunks per warp per tile
     if constexpr (kMode == kModeSample) {
       // ---- sample pass: maxima of chunk_w consecutive sample columns, no per-row state ----
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -199,16 +230,16 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
           ptx::mbar_wait(&tfull_bar[acc], aphase);
           ptx::tc_fence_after();
-          const int64_t gbase = static_cast<int64_t>(t) * kBlockN;
-          const bool full_tile = gbase + kBlockN <= p.ng;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN;
-          float m8[kBlockN / 8];  // maxima of 8-column groups of this tile
+          const int64_t gbase = static_cast<int64_t>(t) * kBlockN + half * kHalfCols;
+          const bool full_tile = gbase + kHalfCols <= p.ng;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN + half * kHalfCols;
+          float m8[kHalfCols / 8];  // maxima of 8-column groups of this half tile
 #pragma unroll
-          for (int c = 0; c < kBlockN / 32; ++c) {
+          for (int c = 0; c < kChunks; ++c) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + c * 32, v);
             ptx::tmem_ld_wait();
-            if (c == kBlockN / 32 - 1) {
+            if (c == kChunks - 1) {
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
@@ -227,67 +258,68 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           if (active) {
             float* dst = p.cmax + q * static_cast<int64_t>(p.num_chunks);
-            const int per8 = p.chunk_w >> 3;          // 1, 2 or 4 groups of 8 per chunk
-            const int nch = kBlockN / p.chunk_w;      // chunks per tile
+            const int per8 = p.chunk_w >> 3;  // 1, 2 or 4 groups of 8 per chunk
             const int c0 = static_cast<int>(gbase / p.chunk_w);
             if (per8 == 1) {
 #pragma unroll
-              for (int i = 0; i < kBlockN / 8; ++i)
+              for (int i = 0; i < kHalfCols / 8; ++i)
                 if (c0 + i < p.num_chunks) dst[c0 + i] = m8[i];
             } else if (per8 == 2) {
 #pragma unroll
-              for (int i = 0; i < kBlockN / 16; ++i)
+              for (int i = 0; i < kHalfCols / 16; ++i)
                 if (c0 + i < p.num_chunks) dst[c0 + i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
             } else {
 #pragma unroll
-              for (int i = 0; i < kBlockN / 32; ++i)
+              for (int i = 0; i < kHalfCols / 32; ++i)
                 if (c0 + i < p.num_chunks)
                   dst[c0 + i] = fmaxf(fmaxf(m8[4 * i], m8[4 * i + 1]), fmaxf(m8[4 * i + 2], m8[4 * i + 3]));
             }
-            (void)nch;
           }
         }
       }
     } else {
       // ---- main pass: TMEM -> threshold filter -> candidate lists ----
       constexpr bool kDump = (kMode == kModeDump);
-      uint32_t* hist = hist_all + ew * 256;
+      uint32_t* hist = reinterpret_cast<uint32_t*>(stage_all + warp * kStageBytesPerWarp);  // idle during a prune
+      const uint32_t stage_lane = ptx::smem_u32(stage_all + warp * kStageBytesPerWarp) + lane * 4;
       const int prune_at = p.cap - 32;
+      const int nlists = p.nsplit * kColHalves;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int split = item / p.num_qt, qt = item - split * p.num_qt;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
         const int64_t q = static_cast<int64_t>(qt) * kBlockM + row;
         const bool active = q < p.nq;
+        const int64_t list = active ? q * nlists + split * kColHalves + half : 0;
         float thr = INFINITY;  // inactive rows (and the benchmark-only 'emit nothing' flag) pass nothing
         if (active && !(p.flags & HCIR_FLAG_NO_EMIT)) thr = p.thr0 ? p.thr0[q] : -INFINITY;
         int cnt = 0;
-        uint64_t* buf = p.keys + (active ? (q * p.nsplit + split) * static_cast<int64_t>(p.cap) : 0);
+        uint64_t* buf = p.keys + list * static_cast<int64_t>(p.cap);
         for (int t = t0; t < t1; ++t, ++iter) {
           const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
           ptx::mbar_wait(&tfull_bar[acc], aphase);
           ptx::tc_fence_after();
-          const int64_t gbase = static_cast<int64_t>(t) * kBlockN;
-          const bool full_tile = gbase + kBlockN <= p.ng;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN;
+          const int64_t gbase = static_cast<int64_t>(t) * kBlockN + half * kHalfCols;
+          const bool full_tile = gbase + kHalfCols <= p.ng;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kBlockN + half * kHalfCols;
 #pragma unroll 1
-          for (int c = 0; c < kBlockN / 32; ++c) {
+          for (int c = 0; c < kChunks; ++c) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + c * 32, v);
             ptx::tmem_ld_wait();
-            if (c == kBlockN / 32 - 1) {
-              // whole accumulator stage is in registers now: hand it back to the MMA warp
+            if (c == kChunks - 1) {
+              // this warp's part of the accumulator stage is in registers: hand it back
               ptx::tc_fence_before();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
             }
             const uint32_t gcol0 = static_cast<uint32_t>(gbase) + c * 32;
             if (full_tile) {
-              scan_chunk<false>(v, thr, buf, cnt, gcol0, 32);
+              scan_chunk<false>(v, thr, buf, cnt, gcol0, 32, stage_lane);
             } else {
               const int64_t rem = p.ng - static_cast<int64_t>(gcol0);
               const int lim = rem >= 32 ? 32 : (rem > 0 ? static_cast<int>(rem) : 0);
-              scan_chunk<true>(v, thr, buf, cnt, gcol0, lim);
+              scan_chunk<true>(v, thr, buf, cnt, gcol0, lim, stage_lane);
             }
             if (kDump && active) {
 #pragma unroll
@@ -313,8 +345,8 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
         }
         if (active) {
-          p.counts[q * p.nsplit + split] = cnt;
-          p.thr_out[q * p.nsplit + split] = thr;
+          p.counts[list] = cnt;
+          p.thr_out[list] = thr;
         }
       }
     }
@@ -322,7 +354,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+  if (warp == kAllocWarp) ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -433,7 +465,9 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
                (long long)ng);
   HCIR_REQUIRE(reinterpret_cast<uintptr_t>(q_bf16) % 16 == 0 && reinterpret_cast<uintptr_t>(g_bf16) % 16 == 0,
                "simtopk: operands must be 16-byte aligned");
-  HCIR_REQUIRE(plan->kc > 0 && plan->cap >= plan->kc + 64 && plan->nsplit > 0, "simtopk: inconsistent plan");
+  HCIR_REQUIRE(plan->kc > 0 && plan->cap >= plan->kc + 64 && plan->nsplit > 0 &&
+                   plan->nlists == plan->nsplit * kColHalves,
+               "simtopk: inconsistent plan");
   int rc = check_device();
   if (rc != HCIR_OK) return rc;
   int dev = 0, sms = 148;
@@ -545,7 +579,7 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   // list capacity: expected appends per (query, split) list with head-room, bounded so that the
   // prune path (not the workspace) absorbs adversarial data
   const int64_t tps = ceil_div_i64(tiles, plan->nsplit);
-  const double mu = pass_rate * static_cast<double>(tps * kBlockN);
+  const double mu = pass_rate * static_cast<double>(tps * kHalfCols);
   int64_t cap = 2 * kc + 32;
   if (S > 0) {
     const int64_t want = static_cast<int64_t>(1.5 * mu) + 96;
@@ -559,11 +593,12 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
     off = (off + bytes + 255) / 256 * 256;
     return at;
   };
-  plan->counts_off = take(static_cast<uint64_t>(nq) * plan->nsplit * sizeof(int32_t));
-  plan->thr_out_off = take(static_cast<uint64_t>(nq) * plan->nsplit * sizeof(float));
+  plan->nlists = plan->nsplit * kColHalves;
+  plan->counts_off = take(static_cast<uint64_t>(nq) * plan->nlists * sizeof(int32_t));
+  plan->thr_out_off = take(static_cast<uint64_t>(nq) * plan->nlists * sizeof(float));
   plan->thr0_off = take(static_cast<uint64_t>(nq) * sizeof(float));
   plan->cmax_off = take(static_cast<uint64_t>(nq) * plan->num_chunks * sizeof(float));
-  plan->keys_off = take(static_cast<uint64_t>(nq) * plan->nsplit * plan->cap * sizeof(uint64_t));
+  plan->keys_off = take(static_cast<uint64_t>(nq) * plan->nlists * plan->cap * sizeof(uint64_t));
   plan->bytes = off;
   return HCIR_OK;
 }

@@ -87,13 +87,13 @@ def test_simtopk_accumulator_tiles_match_fp32_matmul(nq, ng, d):
     err = (scores.double() - ref).abs().max().item()
     assert err < 2e-6, f"max |tile - ref| = {err}"
     # candidate lists: a superset of the top-kc by these scores
-    counts = ws[: nq * plan.nsplit * 4].view(torch.int32).view(nq, plan.nsplit).cpu().numpy()
-    keys = ws[plan.keys_off:].view(torch.int64).view(nq, plan.nsplit, plan.cap).cpu().numpy()
+    counts = ws[: nq * plan.nlists * 4].view(torch.int32).view(nq, plan.nlists).cpu().numpy()
+    keys = ws[plan.keys_off:].view(torch.int64).view(nq, plan.nlists, plan.cap).cpu().numpy()
     sc = scores.cpu().numpy()
     kk = min(kc, ng)
     for r in range(0, nq, max(1, nq // 16)):
         cand = set()
-        for s in range(plan.nsplit):
+        for s in range(plan.nlists):
             ks = keys[r, s, : counts[r, s]].astype(np.uint64)
             cand |= set((0xFFFFFFFF - (ks & np.uint64(0xFFFFFFFF))).astype(np.int64).tolist())
         kth = np.sort(sc[r])[::-1][kk - 1]

@@ -1,39 +1,73 @@
-"""Micro-benchmark of the simtopk kernel alone (CUDA events), optionally with the candidate
-emission disabled (plan.reserved bit 0) to expose the pure tcgen05 contraction throughput."""
-import sys, os
+"""Micro-benchmark of the simtopk call (sample pass + thresholds + main pass) with CUDA events per
+iteration.  flags: HCIR_FLAG_* (1 = emit nothing, 4 = main pass only, 8 = never skip a chunk).
+Prints min / median per-iteration time and the SM clock sampled while the loop runs."""
+import sys, os, threading, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 import torch
 import hcir_b200
 from hcir_b200 import _lib
 from hcir_b200.engine import l2_normalize
 
-def run(nq, ng, d, kc, flags, nsplit=None, iters=10):
+try:
+    import pynvml
+    pynvml.nvmlInit()
+    _H = pynvml.nvmlDeviceGetHandleByIndex(0)
+except Exception:
+    _H = None
+
+_DATA = {}
+
+def data(nq, ng, d):
+    key = (nq, ng, d)
+    if key not in _DATA:
+        _DATA.clear()
+        g = torch.Generator(device="cuda").manual_seed(1)
+        q = torch.randn(nq, d, device="cuda", generator=g); b = torch.randn(ng, d, device="cuda", generator=g)
+        _, qbf, _ = l2_normalize(q, want_f32=False, want_delta=False)
+        _, gbf, _ = l2_normalize(b, want_f32=False, want_delta=False)
+        _DATA[key] = (qbf, gbf)
+    return _DATA[key]
+
+def run(nq, ng, d, kc, flags, iters=20):
     lib = _lib.load()
-    q = torch.randn(nq, d, device="cuda"); g = torch.randn(ng, d, device="cuda")
-    _, qbf, _ = l2_normalize(q, want_f32=False, want_delta=False)
-    _, gbf, _ = l2_normalize(g, want_f32=False, want_delta=False)
+    qbf, gbf = data(nq, ng, d)
     ld = qbf.shape[1]
     plan = _lib.Plan()
     _lib.check(lib.hcir_simtopk_plan(nq, ng, ld, kc, 148, plan))
-    plan.flags = flags
     ws = torch.empty(int(plan.bytes), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    call = lambda: _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, gbf.data_ptr(), ng, ld, plan, ws.data_ptr(), st))
+    call()                       # thresholds in the workspace (needed by MAIN_ONLY)
+    plan.flags = flags
     for _ in range(3):
-        _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, gbf.data_ptr(), ng, ld, plan, ws.data_ptr(), st))
+        call()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
-        _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, gbf.data_ptr(), ng, ld, plan, ws.data_ptr(), st))
-    b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / iters
-    tf = 2.0 * nq * ng * ld / ms / 1e9
-    print(f"nq={nq} ng={ng} d={d} kc={kc} flags={flags} nsplit={plan.nsplit}: {ms:.3f} ms  {tf:.1f} TFLOP/s  "
-          f"gallery {ng*ld*2/ms/1e6:.0f} GB/s", flush=True)
+    clocks, stop = [], threading.Event()
+    def sample():
+        while not stop.is_set():
+            if _H is not None:
+                clocks.append(pynvml.nvmlDeviceGetClockInfo(_H, pynvml.NVML_CLOCK_SM))
+            time.sleep(0.002)
+    th = threading.Thread(target=sample); th.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record(); call(); b.record()
+    torch.cuda.synchronize(); stop.set(); th.join()
+    ts = np.array([a.elapsed_time(b) for a, b in evs])
+    tf = lambda ms: 2.0 * nq * ng * ld / ms / 1e9
+    clk = int(np.median(clocks)) if clocks else -1
+    print(f"nq={nq} ng={ng} d={d} kc={kc} flags={flags} nsplit={plan.nsplit} cap={plan.cap}: min {ts.min():.3f} ms "
+          f"({tf(ts.min()):.0f} TF)  med {np.median(ts):.3f} ms ({tf(np.median(ts)):.0f} TF)  "
+          f"gallery {ng*ld*2/np.median(ts)/1e6:.0f} GB/s  sm_clk {clk} MHz", flush=True)
 
 if __name__ == "__main__":
-    for flags in (1, 0):
-        run(10000, 200000, 768, 104, flags)
-        run(4096, 1000000, 768, 264, flags)
-        run(64, 2000000, 768, 104, flags)
-        run(16384, 200000, 2048, 464, flags)
+    if len(sys.argv) > 1:
+        for flags in [int(x) for x in sys.argv[1:]]:
+            run(10000, 200000, 768, 104, flags)
+    else:
+        for flags in (5, 4):
+            run(10000, 200000, 768, 104, flags)
+            run(4096, 1000000, 768, 264, flags)
+            run(64, 2000000, 768, 104, flags)
+            run(16384, 200000, 2048, 464, flags)
