@@ -78,7 +78,7 @@ int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, float* out_f
  *                    >= thr0[q], so nothing <= thr0[q] can be a top-kc candidate;
  *   3. main pass     full contraction; the epilogue compares every accumulator value with the
  *                    query's threshold and appends the survivors (64-bit keys) to one list per
- *                    (query, gallery split, tile column half).  A list that fills up is pruned back to its kc
+ *                    (query, gallery split).  A list that fills up is pruned back to its kc
  *                    best in place and its threshold raised (rare).
  * Output: for every query and split a list of at most `cap` candidate KEYS (bf16-contraction
  * scores) and the threshold the list ended with, such that every gallery row of that split
@@ -98,7 +98,7 @@ typedef struct {
   int32_t chunk_w;       /* 8, 16 or 32 sample columns per chunk maximum                   */
   int32_t num_chunks;    /* sample_rows / chunk_w                                          */
   int32_t sample_nsplit; /* splits of the sample pass                                      */
-  int32_t nlists;        /* candidate lists per query = 2 * nsplit (one per tile column half) */
+  int32_t nlists;        /* candidate lists per query (= nsplit x column slices per tile)    */
   uint64_t counts_off, thr_out_off, thr0_off, cmax_off, keys_off;
   uint64_t bytes;        /* total workspace bytes                                          */
 } hcir_plan_t;

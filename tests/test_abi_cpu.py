@@ -56,7 +56,7 @@ def test_plan_is_consistent():
         tps = -(-tiles // p.nsplit)
         assert -(-tiles // tps) == p.nsplit, "empty split"
         assert p.cap >= p.kc + 64 and p.cap % 32 == 0 and p.cap <= max(2 * p.kc + 64, 8 * p.kc)
-        assert p.nlists == 2 * p.nsplit
+        assert p.nlists == p.nsplit  # one list per (query, split): kColHalves == 1
         assert p.bytes >= p.keys_off + nq * p.nlists * p.cap * 8
         assert p.keys_off % 256 == 0 and p.cmax_off % 256 == 0
         if p.sample_rows:
