@@ -17,8 +17,10 @@ class Plan(C.Structure):
     _fields_ = [("nsplit", C.c_int32), ("cap", C.c_int32), ("kc", C.c_int32), ("flags", C.c_int32),
                 ("sample_rows", C.c_int32), ("sample_stride", C.c_int32), ("chunk_w", C.c_int32),
                 ("num_chunks", C.c_int32), ("sample_nsplit", C.c_int32), ("nlists", C.c_int32),
+                ("hint_rank", C.c_int32), ("reserved", C.c_int32),
                 ("counts_off", C.c_uint64), ("thr_out_off", C.c_uint64), ("thr0_off", C.c_uint64),
-                ("cmax_off", C.c_uint64), ("keys_off", C.c_uint64), ("bytes", C.c_uint64)]
+                ("thr_hi_off", C.c_uint64), ("cmax_off", C.c_uint64), ("keys_off", C.c_uint64),
+                ("bytes", C.c_uint64)]
 
     def kernels(self) -> int:
         """CUDA kernels one hcir_simtopk call enqueues with this plan."""
@@ -77,7 +79,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here == ABI/header drift
         fn.restype = res
         fn.argtypes = args
-    if lib.hcir_abi_version() != 2:
+    if lib.hcir_abi_version() != 3:
         raise RuntimeError("hcir_b200: ABI version mismatch")
     _lib = lib
     return lib

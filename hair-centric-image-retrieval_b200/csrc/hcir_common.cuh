@@ -89,6 +89,34 @@ __device__ __forceinline__ float canonical_dot(const float4* __restrict__ q4,
   return acc;
 }
 
+// Two rows at once (same per-row arithmetic order as canonical_dot, so bit-identical results):
+// twice the loads in flight per lane for the latency-bound row gathers of the re-score.
+__device__ __forceinline__ void canonical_dot2(const float4* __restrict__ q4, const float4* __restrict__ ga,
+                                               const float4* __restrict__ gb, int ld4, int lane, float& sa,
+                                               float& sb) {
+  float a = 0.0f, b = 0.0f;
+  for (int c = lane; c < ld4; c += kWarp) {
+    const float4 x = q4[c];
+    const float4 y = __ldg(ga + c);
+    const float4 z = __ldg(gb + c);
+    a = fmaf(x.x, y.x, a);
+    a = fmaf(x.y, y.y, a);
+    a = fmaf(x.z, y.z, a);
+    a = fmaf(x.w, y.w, a);
+    b = fmaf(x.x, z.x, b);
+    b = fmaf(x.y, z.y, b);
+    b = fmaf(x.z, z.z, b);
+    b = fmaf(x.w, z.w, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(kFull, a, o);
+    b += __shfl_xor_sync(kFull, b, o);
+  }
+  sa = a;
+  sb = b;
+}
+
 // ---- warp-cooperative exact selection ("prune") -----------------------------------------
 // Keep the `keep` largest of the `cnt` (> keep) unique keys in buf[0..cnt) -- a buffer in
 // GLOBAL memory (L2 resident) -- compacted in place to buf[0..keep) in arbitrary order.
@@ -240,6 +268,77 @@ __device__ inline uint64_t block_select(const uint64_t* keys, int cnt, int keep,
     __syncthreads();
   }
   return thr;
+}
+
+// ---- block-cooperative k-th largest of 32-bit ordered values ------------------------------------
+// vals[0..n) in shared memory (not modified), 1 <= k <= n.  Returns the k-th largest VALUE to every
+// thread (ties are fine: duplicates count).  Linear 256-bin histogram over [lo, hi], narrowed to the
+// bin that holds the k-th largest until the bin is one value wide -- two passes for typical score
+// distributions, where the MSB-first radix select needs four or eight.  `hist` = 256 words,
+// `scratch` = 4 words of shared memory.  The whole block must call it convergently.
+__device__ inline uint32_t block_kth_u32(const uint32_t* vals, int n, int k, uint32_t* hist, uint32_t* scratch) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  if (tid == 0) { scratch[0] = 0xFFFFFFFFu; scratch[1] = 0u; }
+  __syncthreads();
+  {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = tid; i < n; i += nthr) { mn = min(mn, vals[i]); mx = max(mx, vals[i]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+      mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+    }
+    if (lane == 0) { atomicMin(&scratch[0], mn); atomicMax(&scratch[1], mx); }
+  }
+  __syncthreads();
+  uint32_t lo = scratch[0], hi = scratch[1], need = static_cast<uint32_t>(k);
+  __syncthreads();
+  while (lo < hi) {
+    const uint32_t span = hi - lo;
+    int shift = 0;
+    while ((span >> shift) >= 256u) ++shift;
+    for (int b = tid; b < 256; b += nthr) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) {
+      const uint32_t v = vals[i];
+      if (v >= lo && v <= hi) atomicAdd(&hist[(v - lo) >> shift], 1u);
+    }
+    __syncthreads();
+    if (tid < kWarp) {  // warp 0 scans from the top bin: lane l owns bins 255-8l .. 248-8l
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - (8 * lane + j)]; sum += c[j]; }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < kWarp; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t excl = incl - sum;
+      if (excl < need && need <= incl) {
+        uint32_t run = excl;
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!done && run + c[j] >= need) {
+            scratch[2] = 255 - (8 * lane + j);
+            scratch[3] = need - run;
+            done = true;
+          }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t b = scratch[2];
+    need = scratch[3];
+    const uint32_t nlo = lo + (b << shift);
+    const uint32_t nhi = (shift == 0) ? nlo : min(hi, nlo + ((1u << shift) - 1u));
+    lo = nlo;
+    hi = nhi;
+    __syncthreads();
+  }
+  return lo;
 }
 
 }  // namespace hcir

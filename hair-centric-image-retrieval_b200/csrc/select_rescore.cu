@@ -1,7 +1,9 @@
 // K3: per-query candidate selection, adaptive fp32 re-score, exact sort, certification.
-// One CTA per query.  Bandwidth-bound: one streaming read of the query's candidate lists
-// (a second one, when the lists exceed the staging buffer, hits L2) plus ~ (k + 16 +
-// near-boundary candidates) fp32 gallery rows of 4*ld bytes; everything else is shared memory.
+// One CTA per query.  Bandwidth / latency-bound: ONE streaming read of the query's candidate
+// lists (the sample pass supplies a staging hint thr_hi[q] that ~4*kc candidates exceed, so
+// the kc best can be picked from a small shared-memory stage without a second pass; a
+// histogram-select fallback covers the cases where the hint is off) plus ~ (k + 16 +
+// near-boundary candidates) fp32 gallery rows of 4*ld bytes.
 #include <math.h>
 
 #include "hcir_common.cuh"
@@ -10,26 +12,24 @@ namespace hcir {
 
 constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / kWarp;
-constexpr int kRound1Slack = 16;
-constexpr int kBins = 2048;       // histogram bins of the streaming selection
-constexpr int kStageExtra = 512;  // staging room beyond kc for the bin that holds the kc-th best
+constexpr int kRound1Slack = 6;
+constexpr int kBins = 2048;  // histogram bins of the fallback streaming selection
 
 struct SelSmem {  // offsets (bytes) into dynamic shared memory
-  size_t stage, sel, fk, qrow, pos, hist, offs, scratch, total;
+  size_t stage, sel, fk, qrow, hist, offs, scratch, total;
   int stage_cap;
 };
 
-static SelSmem sel_smem_layout(int nsplit, int kc, int ld) {
+static SelSmem sel_smem_layout(int nlists, int kc, int ld) {
   SelSmem L;
-  L.stage_cap = kc + kStageExtra;
+  L.stage_cap = (8 * kc > 1024) ? 8 * kc : 1024;
   size_t o = 0;
   L.stage = o; o += static_cast<size_t>(L.stage_cap) * 8;
   L.sel = o; o += static_cast<size_t>(kc) * 8;
   L.fk = o; o += static_cast<size_t>(kc) * 8;
   L.qrow = o; o += static_cast<size_t>(ld) * 4;
-  L.pos = o; o += static_cast<size_t>(kc) * 4;
   L.hist = o; o += kBins * 4;
-  L.offs = o; o += (static_cast<size_t>(nsplit) + 1) * 4;
+  L.offs = o; o += (static_cast<size_t>(nlists) + 1) * 4;
   o = (o + 15) / 16 * 16;
   L.scratch = o; o += 32 * 4;
   L.total = o;
@@ -41,10 +41,10 @@ static SelSmem sel_smem_layout(int nsplit, int kc, int ld) {
 // (the visitor has shared-memory side effects the compiler will not hoist loads across).
 constexpr int kKeyBatch = 8;
 template <typename F>
-__device__ __forceinline__ void for_each_key(const uint64_t* __restrict__ lists, const int32_t* offs, int nsplit,
+__device__ __forceinline__ void for_each_key(const uint64_t* __restrict__ lists, const int32_t* cnts, int nlists,
                                              int cap, int warp, int lane, F&& f) {
-  for (int s = warp; s < nsplit; s += kSelWarps) {
-    const int c = offs[s + 1] - offs[s];
+  for (int s = warp; s < nlists; s += kSelWarps) {
+    const int c = cnts[s];
     const uint64_t* src = lists + static_cast<int64_t>(s) * cap;
     for (int base = 0; base < c; base += kWarp * kKeyBatch) {
       uint64_t kk[kKeyBatch];
@@ -60,86 +60,128 @@ __device__ __forceinline__ void for_each_key(const uint64_t* __restrict__ lists,
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+// rank (number of strictly greater keys) of every key[0..n) -> dst[rank] = key for rank < keep.
+// Keys are unique, so ranks are a permutation.  The caller syncs.
+__device__ __forceinline__ void rank_scatter(const uint64_t* keys, int n, uint64_t* dst, int keep, int tid) {
+  for (int j = tid; j < n; j += kSelThreads) {
+    const uint64_t mine = keys[j];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) rank += (keys[i] > mine) ? 1 : 0;
+    if (rank < keep) dst[rank] = mine;
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads, 5)
 select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int ld, int64_t nq,
-                      int64_t ng, int k, int64_t idx_offset, int nsplit, int cap, int kc,
+                      int64_t ng, int k, int64_t idx_offset, int nlists, int cap, int kc,
                       const int32_t* __restrict__ counts, const uint64_t* __restrict__ cand,
-                      const float* __restrict__ thr_out, const float* __restrict__ q_delta,
-                      float g_delta_max, float eps_acc, float* __restrict__ out_sim,
-                      int64_t* __restrict__ out_idx, int32_t* __restrict__ uncert_list,
-                      int32_t* __restrict__ uncert_count, SelSmem L) {
+                      const float* __restrict__ thr_out, const float* __restrict__ thr_hi,
+                      const float* __restrict__ q_delta, float g_delta_max, float eps_acc,
+                      float* __restrict__ out_sim, int64_t* __restrict__ out_idx,
+                      int32_t* __restrict__ uncert_list, int32_t* __restrict__ uncert_count, SelSmem L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw + L.stage);
-  uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw + L.sel);
-  uint64_t* fk = reinterpret_cast<uint64_t*>(smem_raw + L.fk);
-  int32_t* pos = reinterpret_cast<int32_t*>(smem_raw + L.pos);
+  uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw + L.sel);   // kc best by bf16 score, DESCENDING
+  uint64_t* fk = reinterpret_cast<uint64_t*>(smem_raw + L.fk);     // fp32 keys of the re-scored prefix of sel
   float* qrow = reinterpret_cast<float*>(smem_raw + L.qrow);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + L.hist);
   int32_t* offs = reinterpret_cast<int32_t*>(smem_raw + L.offs);
-  uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + L.scratch);  // [0..3] block_select, [4..] ours
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + L.scratch);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q = blockIdx.x;
   const int ld4 = ld >> 2;
-  const uint64_t* lists = cand + q * nsplit * static_cast<int64_t>(cap);
+  const uint64_t* lists = cand + q * nlists * static_cast<int64_t>(cap);
 
-  // ---- stage the fp32 query row; prefix-sum the list lengths; largest list threshold --------
+  // ---- start: issue the query-row loads (consumed after the key pass); every warp fetches the
+  // lengths / thresholds of ITS lists (w, w+8, ...) and goes straight to reading keys -- there is
+  // no serial prefix phase; totals are combined with shared-memory atomics -----------------------
+  constexpr int kQv = 2;  // float4 per thread held in registers: covers ld <= 2048 (the rest is loaded late)
+  float4 qv[kQv];
   {
     const float4* src = reinterpret_cast<const float4*>(q32 + q * static_cast<int64_t>(ld));
-    for (int c = tid; c < ld4; c += kSelThreads) reinterpret_cast<float4*>(qrow)[c] = __ldg(src + c);
-  }
-  if (warp == 0) {
-    int run = 0;
-    float tmax = -INFINITY, tmin = INFINITY;
-    for (int base = 0; base < nsplit; base += kWarp) {
-      const int s = base + lane;
-      const int c = (s < nsplit) ? counts[q * nsplit + s] : 0;
-      if (s < nsplit) {
-        const float t = thr_out[q * nsplit + s];
-        tmax = fmaxf(tmax, t);
-        tmin = fminf(tmin, t);
-      }
-      int incl = c;
 #pragma unroll
-      for (int o = 1; o < kWarp; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (s < nsplit) offs[s + 1] = run + incl;
-      run += __shfl_sync(kFull, incl, kWarp - 1);
+    for (int u = 0; u < kQv; ++u) {
+      const int c = tid + u * kSelThreads;
+      if (c < ld4) qv[u] = __ldg(src + c);
+    }
+  }
+  if (tid == 0) {
+    scratch[5] = 0;
+    scratch[6] = 0;
+    scratch[7] = 0;
+    scratch[9] = 0;             // staged count
+    scratch[13] = 0;            // keys outside the assumed score range
+    scratch[14] = 0xFFFFFFFFu;  // smallest list threshold (ordered bits)
+    scratch[18] = 0;            // total candidates
+    scratch[19] = 0;            // largest list threshold (ordered bits)
+  }
+  __syncthreads();
+  {
+    int tot = 0;
+    uint32_t omax = 0u, omin = 0xFFFFFFFFu;
+    for (int s = warp + kSelWarps * lane; s < nlists; s += kSelWarps * kWarp) {
+      const int c = counts[q * nlists + s];
+      offs[s] = c;
+      tot += c;
+      const uint32_t o = f2ord(thr_out[q * nlists + s]);
+      omax = max(omax, o);
+      omin = min(omin, o);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      tmax = fmaxf(tmax, __shfl_xor_sync(kFull, tmax, o));
-      tmin = fminf(tmin, __shfl_xor_sync(kFull, tmin, o));
+      tot += __shfl_xor_sync(kFull, tot, o);
+      omax = max(omax, __shfl_xor_sync(kFull, omax, o));
+      omin = min(omin, __shfl_xor_sync(kFull, omin, o));
     }
     if (lane == 0) {
-      offs[0] = 0;
-      scratch[8] = __float_as_uint(tmax);
-      scratch[9] = 0;   // staged count
-      scratch[13] = 0;  // keys above the assumed score range
-      scratch[14] = __float_as_uint(tmin);
+      atomicAdd(&scratch[18], static_cast<uint32_t>(tot));
+      atomicMax(&scratch[19], omax);
+      atomicMin(&scratch[14], omin);
     }
+    __syncwarp();  // this warp's offs[] entries are visible to its own lanes
   }
-  __syncthreads();
-  const int total = offs[nsplit];
-  // rows that are in no list score <= the threshold their list ended with (bf16 contraction)
-  float tprime = __uint_as_float(scratch[8]);
-  const bool all_in = (static_cast<int64_t>(total) == ng);
 
   // ---- gather the candidates that can be among the kc best (by bf16 score) into `stage` ------
-  int nstage;
-  if (total <= L.stage_cap) {
-    for_each_key(lists, offs, nsplit, cap, warp, lane, [&](uint64_t key) { stage[atomicAdd(&scratch[9], 1u)] = key; });
+  // fast path: one pass, keep what exceeds the staging hint (or everything, if it all fits)
+  // (the hint is "stage everything" when there was no sample pass)
+  const uint32_t hint = thr_hi ? f2ord(thr_hi[q]) : 0u;
+  int nstage = 0;
+  bool staged = false;
+  {
+    for_each_key(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
+      if (static_cast<uint32_t>(key >> 32) > hint) {
+        const uint32_t at = atomicAdd(&scratch[9], 1u);
+        if (at < static_cast<uint32_t>(L.stage_cap)) stage[at] = key;
+      }
+    });
+    // the query row goes to shared memory now that the key loads have been issued
+#pragma unroll
+    for (int u = 0; u < kQv; ++u) {
+      const int c = tid + u * kSelThreads;
+      if (c < ld4) reinterpret_cast<float4*>(qrow)[c] = qv[u];
+    }
+    for (int c = tid + kQv * kSelThreads; c < ld4; c += kSelThreads)
+      reinterpret_cast<float4*>(qrow)[c] = __ldg(reinterpret_cast<const float4*>(q32 + q * static_cast<int64_t>(ld)) + c);
     __syncthreads();
-    nstage = total;
-  } else {
-    // streaming selection on the ordered similarity bits: kBins linear bins over [lo, hi],
-    // narrowed to the bin that holds the kc-th best until that bin fits the staging buffer.
-    // Every key exceeds the smallest list threshold, and unit bf16 rows score <= ~1.008, which
-    // makes the first pass effective; the full range is the fallback if either bound is moot.
-    const float tmin = __uint_as_float(scratch[14]);
-    uint32_t lo = (tmin > -INFINITY) ? f2ord(tmin) : 0u;
+    const int got = static_cast<int>(scratch[9]);
+    // usable iff nothing was dropped and the kc best are all in the stage
+    staged = (got <= L.stage_cap) && (got >= kc || got == static_cast<int>(scratch[18]));
+    nstage = got;
+    __syncthreads();
+  }
+  const int total = static_cast<int>(scratch[18]);
+  // rows that are in no list score <= the threshold their list ended with (bf16 contraction)
+  float tprime = ord2f(scratch[19]);
+  const bool all_in = (static_cast<int64_t>(total) == ng);
+  if (!staged) {
+    // fallback: streaming selection on the ordered similarity bits -- kBins linear bins over
+    // [lo, hi], narrowed to the bin that holds the kc-th best until that bin fits the stage.
+    // Every key exceeds the smallest list threshold and unit bf16 rows score <= ~1.008, which
+    // makes the first pass effective; the full range is used if either bound is moot.
+    if (tid == 0) scratch[9] = 0;
+    const float tmin = ord2f(scratch[14]);
+    uint32_t lo = (tmin > -INFINITY) ? scratch[14] : 0u;
     uint32_t hi = (tmin > -INFINITY) ? f2ord(1.01f) : 0xFFFFFFFFu;
     bool check_range = (hi != 0xFFFFFFFFu);
     uint32_t above = 0u, cut = 0u;
@@ -149,7 +191,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       while ((span >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
       for (int b = tid; b < kBins; b += kSelThreads) hist[b] = 0;
       __syncthreads();
-      for_each_key(lists, offs, nsplit, cap, warp, lane, [&](uint64_t key) {
+      for_each_key(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
         const uint32_t o = static_cast<uint32_t>(key >> 32);
         if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
         else if (check_range) scratch[13] = 1u;
@@ -201,7 +243,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     }
     // collect everything at or above the cut (exact ties beyond the staging room are dropped:
     // they score == the kc-th best, which the certification bound below covers)
-    for_each_key(lists, offs, nsplit, cap, warp, lane, [&](uint64_t key) {
+    for_each_key(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
       if (static_cast<uint32_t>(key >> 32) >= cut) {
         const uint32_t at = atomicAdd(&scratch[9], 1u);
         if (at < static_cast<uint32_t>(L.stage_cap)) stage[at] = key;
@@ -211,71 +253,130 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     nstage = min(static_cast<int>(scratch[9]), L.stage_cap);
   }
 
-  // ---- keep the kc best by bf16 score --------------------------------------------------------
-  int ncand;
-  if (nstage > kc) {
-    const uint64_t thr_c = block_select(stage, nstage, kc, sel, hist, scratch);
-    tprime = fmaxf(tprime, key_sim(thr_c));
-    ncand = kc;
-  } else {
-    for (int i = tid; i < nstage; i += kSelThreads) sel[i] = stage[i];
-    ncand = nstage;
+  // ---- the kc best by bf16 score, in descending order -----------------------------------------
+  // The stage holds a superset of the kc best.  Rank counting is O(n^2), so a stage much larger
+  // than kc is first cut down with one shared-memory histogram over its own score range.
+  const int ncand = nstage < kc ? nstage : kc;
+  const uint64_t* pool = stage;
+  int npool = nstage;
+  if (nstage > kc + 128) {
+    uint64_t* compact = reinterpret_cast<uint64_t*>(hist);  // the histogram's memory, reused after the scan
+    constexpr int kCompactCap = kBins * 4 / 8;
+    if (tid == 0) { scratch[15] = 0xFFFFFFFFu; scratch[16] = 0u; scratch[17] = 0u; }
+    __syncthreads();
+    {  // score range of the stage
+      uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+      for (int i = tid; i < nstage; i += kSelThreads) {
+        const uint32_t o = static_cast<uint32_t>(stage[i] >> 32);
+        mn = min(mn, o);
+        mx = max(mx, o);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+        mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+      }
+      if (lane == 0) { atomicMin(&scratch[15], mn); atomicMax(&scratch[16], mx); }
+    }
+    for (int b = tid; b < kBins; b += kSelThreads) hist[b] = 0;
+    __syncthreads();
+    const uint32_t lo = scratch[15], span = scratch[16] - lo;
+    int shift = 0;
+    while ((span >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
+    for (int i = tid; i < nstage; i += kSelThreads)
+      atomicAdd(&hist[(static_cast<uint32_t>(stage[i] >> 32) - lo) >> shift], 1u);
+    __syncthreads();
+    if (warp == 0) {  // bin that holds the kc-th best, scanning from the top
+      constexpr int per = kBins / kWarp;
+      uint32_t sum = 0;
+      for (int j = 0; j < per; ++j) sum += hist[kBins - 1 - (per * lane + j)];
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < kWarp; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t need = static_cast<uint32_t>(kc), excl = incl - sum;
+      if (excl < need && need <= incl) {
+        uint32_t run = excl;
+        for (int j = 0; j < per; ++j) {
+          const int b = kBins - 1 - (per * lane + j);
+          if (run + hist[b] >= need) {
+            scratch[10] = static_cast<uint32_t>(b);
+            scratch[11] = run + hist[b];  // keys at or above the cut
+            break;
+          }
+          run += hist[b];
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t cut = lo + (scratch[10] << shift);
+    const int keep = static_cast<int>(scratch[11]);
+    __syncthreads();  // everyone has read the scan result: the histogram memory may be reused
+    if (keep <= kCompactCap) {
+      for (int i = tid; i < nstage; i += kSelThreads) {
+        const uint64_t key = stage[i];
+        if (static_cast<uint32_t>(key >> 32) >= cut) compact[atomicAdd(&scratch[17], 1u)] = key;
+      }
+      __syncthreads();
+      pool = compact;
+      npool = keep;
+    }
   }
-  for (int i = tid; i < ncand; i += kSelThreads) fk[i] = 0ull;
-  if (tid == 0) { scratch[4] = 0; scratch[5] = 0; scratch[6] = 0; scratch[7] = 0; }
+  rank_scatter(pool, npool, sel, kc, tid);
   __syncthreads();
+  if (nstage > kc) tprime = fmaxf(tprime, key_sim(sel[kc - 1]));
 
   const float dq = q_delta ? q_delta[q] : 0.0f;
   const float eps = g_delta_max * (1.0f + dq) + dq * (1.0f + 1e-6f) + eps_acc;
 
+  // fp32 re-score of sel[a..b): two rows per warp step
+  auto rescore = [&](int a, int b) {
+    const float4* q4 = reinterpret_cast<const float4*>(qrow);
+    for (int j = a + 2 * warp; j < b; j += 2 * kSelWarps) {
+      const uint32_t r0 = key_idx(sel[j]);
+      const bool two = (j + 1 < b);
+      const uint32_t r1 = two ? key_idx(sel[j + 1]) : r0;
+      float s0, s1;
+      canonical_dot2(q4, reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(r0) * ld),
+                     reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(r1) * ld), ld4, lane, s0, s1);
+      if (lane == 0) {
+        fk[j] = make_key(s0, r0);
+        if (two) fk[j + 1] = make_key(s1, r1);
+      }
+    }
+  };
+
   // ---- round 1: the k + slack best bf16 candidates ----------------------------------------
-  const int k1 = (ncand < k + kRound1Slack) ? ncand : k + kRound1Slack;
-  uint64_t thr1 = 0ull;
-  if (ncand > k1) thr1 = block_select(sel, ncand, k1, nullptr, hist, scratch);
-  for (int j = tid; j < ncand; j += kSelThreads) {
-    if (sel[j] >= thr1) pos[atomicAdd(&scratch[4], 1u)] = j;
-  }
-  __syncthreads();
-  const int n1 = static_cast<int>(scratch[4]);
-  for (int t = warp; t < n1; t += kSelWarps) {
-    const int j = pos[t];
-    const uint32_t row = key_idx(sel[j]);
-    const float s = canonical_dot(reinterpret_cast<const float4*>(qrow),
-                                  reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(row) * ld), ld4, lane);
-    if (lane == 0) fk[j] = make_key(s, row);
-  }
+  const int n1 = (ncand < k + kRound1Slack) ? ncand : k + kRound1Slack;
+  rescore(0, n1);
   __syncthreads();
   // k-th best fp32 score so far (a lower bound of the final k-th best)
   for (int t = tid; t < n1; t += kSelThreads) {
-    const uint64_t mine = fk[pos[t]];
+    const uint64_t mine = fk[t];
     int rank = 0;
-    for (int i = 0; i < n1; ++i) rank += (fk[pos[i]] > mine) ? 1 : 0;
+    for (int i = 0; i < n1; ++i) rank += (fk[i] > mine) ? 1 : 0;
     if (rank == k - 1) scratch[5] = __float_as_uint(key_sim(mine));
   }
   __syncthreads();
   const float sk1 = (n1 >= k) ? __uint_as_float(scratch[5]) : -INFINITY;
 
-  // ---- round 2: every other candidate whose bf16 score could still reach the top-k -------
-  for (int j = tid; j < ncand; j += kSelThreads) {
-    if (sel[j] < thr1 && key_sim(sel[j]) + eps >= sk1) pos[n1 + atomicAdd(&scratch[6], 1u)] = j;
+  // ---- round 2: every other candidate whose bf16 score could still reach the top-k --------
+  // sel is sorted by bf16 score, so these form a prefix [n1, n1 + n2)
+  for (int j = n1 + tid; j < ncand; j += kSelThreads) {
+    if (key_sim(sel[j]) + eps >= sk1) atomicAdd(&scratch[6], 1u);
   }
   __syncthreads();
-  const int n2 = static_cast<int>(scratch[6]);
-  for (int t = warp; t < n2; t += kSelWarps) {
-    const int j = pos[n1 + t];
-    const uint32_t row = key_idx(sel[j]);
-    const float s = canonical_dot(reinterpret_cast<const float4*>(qrow),
-                                  reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(row) * ld), ld4, lane);
-    if (lane == 0) fk[j] = make_key(s, row);
-  }
+  const int nr = n1 + static_cast<int>(scratch[6]);
+  rescore(n1, nr);
   __syncthreads();
 
   // ---- exact order of the re-scored set, emit top-k ---------------------------------------
-  const int nr = n1 + n2;
   for (int t = tid; t < nr; t += kSelThreads) {
-    const uint64_t mine = fk[pos[t]];
+    const uint64_t mine = fk[t];
     int rank = 0;
-    for (int i = 0; i < nr; ++i) rank += (fk[pos[i]] > mine) ? 1 : 0;
+    for (int i = 0; i < nr; ++i) rank += (fk[i] > mine) ? 1 : 0;
     if (rank < k) {
       const float s = key_sim(mine);
       out_sim[q * k + rank] = s;
@@ -318,9 +419,10 @@ extern "C" int hcir_select_rescore(const float* q_f32, const float* g_f32, int l
   const int32_t* counts = reinterpret_cast<const int32_t*>(ws + plan->counts_off);
   const uint64_t* cand = reinterpret_cast<const uint64_t*>(ws + plan->keys_off);
   const float* thr_out = reinterpret_cast<const float*>(ws + plan->thr_out_off);
+  const float* thr_hi = plan->sample_rows > 0 ? reinterpret_cast<const float*>(ws + plan->thr_hi_off) : nullptr;
   select_rescore_kernel<<<static_cast<unsigned>(nq), kSelThreads, L.total, static_cast<cudaStream_t>(stream)>>>(
-      q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, q_delta,
-      g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
+      q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi,
+      q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
   HCIR_CUDA_TRY(cudaGetLastError());
   return HCIR_OK;
 }

@@ -361,24 +361,36 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // threshold kernel: thr0[q] = kc-th largest chunk maximum of the sample pass.  Every chunk
 // maximum is the score of a distinct real gallery row, so at least kc rows score >= thr0[q]:
 // the main pass may drop everything <= thr0[q] without losing a top-kc candidate.
+// thr_hi[q] = hint_rank-th largest chunk maximum: a staging hint for K3 -- about 4*kc gallery
+// rows are expected to exceed it (performance only; K3 verifies it and falls back if not).
 // grid nq, block 128, dynamic smem: num_chunks keys + hist + scratch.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-threshold_kernel(const float* __restrict__ cmax, int num_chunks, int kc, float* __restrict__ thr0) {
+constexpr int kThrThreads = 128;
+
+__global__ void __launch_bounds__(kThrThreads)
+threshold_kernel(const float* __restrict__ cmax, int num_chunks, int kc, int hint_rank,
+                 float* __restrict__ thr0, float* __restrict__ thr_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(keys + num_chunks);
+  uint32_t* vals = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* hist = vals + num_chunks;
   uint32_t* scratch = hist + 256;
   const int64_t q = blockIdx.x;
   const float* src = cmax + q * static_cast<int64_t>(num_chunks);
-  for (int i = threadIdx.x; i < num_chunks; i += blockDim.x) keys[i] = make_key(src[i], static_cast<uint32_t>(i));
+  for (int i = threadIdx.x; i < num_chunks; i += kThrThreads) vals[i] = f2ord(src[i]);
   __syncthreads();
   if (num_chunks < kc) {
-    if (threadIdx.x == 0) thr0[q] = -INFINITY;
+    if (threadIdx.x == 0) {
+      thr0[q] = -INFINITY;
+      thr_hi[q] = -INFINITY;
+    }
     return;
   }
-  const uint64_t t = block_select(keys, num_chunks, kc, nullptr, hist, scratch);
-  if (threadIdx.x == 0) thr0[q] = key_sim(t);
+  const uint32_t t = block_kth_u32(vals, num_chunks, kc, hist, scratch);
+  const uint32_t h = block_kth_u32(vals, num_chunks, hint_rank, hist, scratch);
+  if (threadIdx.x == 0) {
+    thr0[q] = ord2f(t);
+    thr_hi[q] = ord2f(h);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -514,11 +526,13 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     rc = launch_mode<kModeSample>(mq, ms, sp, sms, st);
     if (rc != HCIR_OK) return rc;
     thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
-    const size_t smem = static_cast<size_t>(plan->num_chunks) * 8 + (256 + 8) * 4;
+    const size_t smem = static_cast<size_t>(plan->num_chunks) * 4 + (256 + 8) * 4;
     HCIR_REQUIRE(smem <= 200 * 1024, "simtopk: %d sample chunks do not fit in shared memory", plan->num_chunks);
     HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    threshold_kernel<<<static_cast<unsigned>(nq), 128, smem, st>>>(sp.cmax, plan->num_chunks, plan->kc, thr0);
+    HCIR_REQUIRE(plan->hint_rank >= 1 && plan->hint_rank <= plan->kc, "simtopk: bad hint_rank=%d", plan->hint_rank);
+    threshold_kernel<<<static_cast<unsigned>(nq), kThrThreads, smem, st>>>(
+        sp.cmax, plan->num_chunks, plan->kc, plan->hint_rank, thr0, reinterpret_cast<float*>(ws + plan->thr_hi_off));
     HCIR_CUDA_TRY(cudaGetLastError());
   }
 
@@ -575,6 +589,9 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
     // kc-th best of m chunk maxima ~ the (-m ln(1 - kc/m))-th best sample row
     const double m = static_cast<double>(plan->num_chunks);
     pass_rate = -m * log(1.0 - kc / m) / static_cast<double>(S);
+    // staging hint for K3: the j-th best sample row, j such that ~4*kc gallery rows beat it
+    int64_t j = (4ll * kc * S + ng - 1) / ng;
+    plan->hint_rank = static_cast<int32_t>(j < 1 ? 1 : (j > kc ? kc : j));
   }
   // list capacity: expected appends per (query, split) list with head-room, bounded so that the
   // prune path (not the workspace) absorbs adversarial data
@@ -597,6 +614,7 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   plan->counts_off = take(static_cast<uint64_t>(nq) * plan->nlists * sizeof(int32_t));
   plan->thr_out_off = take(static_cast<uint64_t>(nq) * plan->nlists * sizeof(float));
   plan->thr0_off = take(static_cast<uint64_t>(nq) * sizeof(float));
+  plan->thr_hi_off = take(static_cast<uint64_t>(nq) * sizeof(float));
   plan->cmax_off = take(static_cast<uint64_t>(nq) * plan->num_chunks * sizeof(float));
   plan->keys_off = take(static_cast<uint64_t>(nq) * plan->nlists * plan->cap * sizeof(uint64_t));
   plan->bytes = off;

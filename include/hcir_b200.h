@@ -35,7 +35,7 @@ extern "C" {
 #define HCIR_ECUDA (-3)      /* a CUDA runtime / driver call failed                        */
 #define HCIR_EWORKSPACE (-4) /* workspace too small                                        */
 
-#define HCIR_ABI_VERSION 2
+#define HCIR_ABI_VERSION 3
 
 /* hcir_plan_t.flags: measurement aids, all 0 in production */
 #define HCIR_FLAG_NO_EMIT 1     /* main pass emits nothing: pure contraction throughput        */
@@ -75,7 +75,9 @@ int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, float* out_f
  *                    (addressed in place through the TMA row stride); the epilogue keeps only
  *                    the maximum of every `chunk_w` consecutive sample columns;
  *   2. thresholds    thr0[q] = kc-th largest chunk maximum: >= kc real gallery rows score
- *                    >= thr0[q], so nothing <= thr0[q] can be a top-kc candidate;
+ *                    >= thr0[q], so nothing <= thr0[q] can be a top-kc candidate; thr_hi[q] =
+ *                    a higher order statistic that ~4*kc gallery rows are expected to beat
+ *                    (a staging hint for hcir_select_rescore, verified there);
  *   3. main pass     full contraction; the epilogue compares every accumulator value with the
  *                    query's threshold and appends the survivors (64-bit keys) to one list per
  *                    (query, gallery split).  A list that fills up is pruned back to its kc
@@ -85,7 +87,7 @@ int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, float* out_f
  * NOT listed scores <= that threshold.
  *
  * hcir_simtopk_plan fills the launch plan and the workspace layout (all offsets in bytes):
- *   int32 counts[nq][nlists]; float thr_out[nq][nlists]; float thr0[nq];
+ *   int32 counts[nq][nlists]; float thr_out[nq][nlists]; float thr0[nq]; float thr_hi[nq];
  *   float cmax[nq][num_chunks]; uint64 keys[nq][nlists][cap]  (RAW keys: fp32 bits << 32 |
  *   0xFFFFFFFF - row; the ordered form of the header comment is applied on load). */
 typedef struct {
@@ -99,7 +101,9 @@ typedef struct {
   int32_t num_chunks;    /* sample_rows / chunk_w                                          */
   int32_t sample_nsplit; /* splits of the sample pass                                      */
   int32_t nlists;        /* candidate lists per query (= nsplit x column slices per tile)    */
-  uint64_t counts_off, thr_out_off, thr0_off, cmax_off, keys_off;
+  int32_t hint_rank;     /* thr_hi[q] = hint_rank-th largest chunk maximum (K3 staging hint) */
+  int32_t reserved;
+  uint64_t counts_off, thr_out_off, thr0_off, thr_hi_off, cmax_off, keys_off;
   uint64_t bytes;        /* total workspace bytes                                          */
 } hcir_plan_t;
 
