@@ -171,8 +171,9 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             // queries are re-read by every gallery tile: keep them in L2; gallery streams once
             ptx::tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * kABytes, kb * kBlockK, qt * kBlockM,
                              ptx::kEvictLast);
+            // one query tile: every gallery byte is used exactly once -> do not keep it in L2
             ptx::tma_load_2d(&tmap_g, &full_bar[stage], smem_b + stage * kBBytes, kb * kBlockK, t * kBlockN,
-                             ptx::kEvictNormal);
+                             p.num_qt == 1 ? ptx::kEvictFirst : ptx::kEvictNormal);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -488,7 +489,9 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
   char* ws = static_cast<char*>(workspace);
 
   CUtensorMap mq, mg;
-  rc = make_bf16_map(&mq, q_bf16, nq, ld, ld, kBlockM);
+  HCIR_REQUIRE(plan->q_rows == 0 || plan->q_rows >= nq, "simtopk: plan.q_rows=%d < nq=%lld", plan->q_rows,
+               (long long)nq);
+  rc = make_bf16_map(&mq, q_bf16, plan->q_rows > 0 ? plan->q_rows : nq, ld, ld, kBlockM);
   if (rc != HCIR_OK) return rc;
 
   SimParams p{};
@@ -578,6 +581,8 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   if (64ll * kc * 16 <= ng) { w = 32; S = 64ll * kc; }
   else if (32ll * kc * 12 <= ng) { w = 16; S = 32ll * kc; }
   else if (16ll * kc * 4 <= ng) { w = 8; S = 16ll * kc; }
+  // a big gallery affords a bigger sample (1/64 of the rows): tighter thresholds, shorter lists
+  if (w == 32 && ng / 64 > S) S = ng / 64;
   double pass_rate = 1.0;
   if (S > 0) {
     S = (S + kBlockN - 1) / kBlockN * kBlockN;  // whole tiles
@@ -599,8 +604,11 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   const double mu = pass_rate * static_cast<double>(tps * kHalfCols);
   int64_t cap = 2 * kc + 32;
   if (S > 0) {
+    // a list that overflows is pruned in place, which is correct but slow: size the lists for the
+    // expected length with head-room, within a 2 GiB budget for all lists together
     const int64_t want = static_cast<int64_t>(1.5 * mu) + 96;
-    const int64_t hi = 8ll * kc;
+    int64_t hi = (2ll << 30) / (static_cast<int64_t>(nq) * plan->nsplit * kColHalves * 8);
+    if (hi < 8ll * kc) hi = 8ll * kc;
     cap = want < cap ? cap : (want > hi ? hi : want);
   }
   plan->cap = round_up_int(static_cast<int>(cap), 32);

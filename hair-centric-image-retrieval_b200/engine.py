@@ -69,10 +69,11 @@ def _to_host(t: torch.Tensor, kind: str):
     return h.numpy() if kind == "numpy" else h
 
 
-def l2_normalize(x: torch.Tensor, *, want_f32=True, want_bf16=True, want_delta=True):
+def l2_normalize(x: torch.Tensor, *, want_f32=True, want_bf16=True, want_delta=True, pad_rows_to: int = 1):
     """K1 on a device tensor [n, d] fp32 -> (unit fp32 [n, ld] | None, unit bf16 [n, ld] | None,
     delta [n] | None) with ld = d rounded up to 64 (zero padded).  ``F.normalize(x, dim=1)``
-    semantics (classification_engine.py:50)."""
+    semantics (classification_engine.py:50).  ``pad_rows_to``: the bf16 output is a view of a
+    zero-padded buffer whose row count is a multiple of it (query side of the contraction)."""
     lib = _lib.load()
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
         raise ValueError("l2_normalize expects a 2-D fp32 CUDA tensor")
@@ -82,7 +83,13 @@ def l2_normalize(x: torch.Tensor, *, want_f32=True, want_bf16=True, want_delta=T
     ld = lib.hcir_padded_dim(d)
     dev = x.device
     o32 = torch.empty((n, ld), dtype=torch.float32, device=dev) if want_f32 else None
-    obf = torch.empty((n, ld), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    obf = None
+    if want_bf16:
+        n_alloc = -(-n // pad_rows_to) * pad_rows_to
+        buf = torch.empty((n_alloc, ld), dtype=torch.bfloat16, device=dev)
+        if n_alloc > n:
+            buf[n:].zero_()
+        obf = buf[:n]
     dl = torch.empty((n,), dtype=torch.float32, device=dev) if want_delta else None
     with torch.cuda.device(dev):
         _lib.check(lib.hcir_l2norm_cast(x.data_ptr(), n, d, x.stride(0),
@@ -208,7 +215,7 @@ class GalleryBank:
         if mode not in ("auto", "tensor", "exact"):
             raise ValueError(f"unknown mode {mode!r}")
         tensor = mode == "tensor" or (mode == "auto" and self.use_tensor_path(nq, k))
-        q32, qbf, qdl = l2_normalize(q, want_bf16=tensor, want_delta=tensor)
+        q32, qbf, qdl = l2_normalize(q, want_bf16=tensor, want_delta=tensor, pad_rows_to=128)
         self.launches += 1
         st = _stream_ptr()
         if not tensor:
@@ -218,6 +225,7 @@ class GalleryBank:
         kc = self.choose_kc(k)
         plan = Plan()
         _lib.check(lib.hcir_simtopk_plan(nq, self.n, self.ld, kc, self.sm_count, plan), "simtopk_plan")
+        plan.q_rows = -(-nq // 128) * 128  # l2_normalize(pad_rows_to=128) allocated them
         ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
         if self.kernel_events is not None and plan.sample_rows > 0:
             # measurement only: enqueue the two phases separately so each gets its own events

@@ -102,7 +102,9 @@ typedef struct {
   int32_t sample_nsplit; /* splits of the sample pass                                      */
   int32_t nlists;        /* candidate lists per query (= nsplit x column slices per tile)    */
   int32_t hint_rank;     /* thr_hi[q] = hint_rank-th largest chunk maximum (K3 staging hint) */
-  int32_t reserved;
+  int32_t q_rows;        /* rows the query buffer really holds (>= nq; 0 = nq).  A buffer padded
+                          * to a multiple of 128 rows keeps the query TMA box in bounds, which
+                          * is measurably faster than TMA out-of-bounds zero fill for small nq */
   uint64_t counts_off, thr_out_off, thr0_off, thr_hi_off, cmax_off, keys_off;
   uint64_t bytes;        /* total workspace bytes                                          */
 } hcir_plan_t;

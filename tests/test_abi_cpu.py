@@ -55,7 +55,8 @@ def test_plan_is_consistent():
         tiles = -(-ng // 256)
         tps = -(-tiles // p.nsplit)
         assert -(-tiles // tps) == p.nsplit, "empty split"
-        assert p.cap >= p.kc + 64 and p.cap % 32 == 0 and p.cap <= max(2 * p.kc + 64, 8 * p.kc)
+        assert p.cap >= p.kc + 64 and p.cap % 32 == 0
+        assert p.cap <= max(2 * p.kc + 64, 8 * p.kc) or nq * p.nlists * p.cap * 8 <= (2 << 30) + 4096 * nq * p.nlists
         assert p.nlists == p.nsplit  # one list per (query, split): kColHalves == 1
         assert p.bytes >= p.keys_off + nq * p.nlists * p.cap * 8
         assert p.keys_off % 256 == 0 and p.cmax_off % 256 == 0
@@ -63,6 +64,7 @@ def test_plan_is_consistent():
             assert p.sample_rows % 256 == 0 and p.chunk_w in (8, 16, 32)
             assert p.num_chunks * p.chunk_w == p.sample_rows and p.num_chunks >= 2 * p.kc
             assert (p.sample_rows - 1) * p.sample_stride < ng and p.sample_rows * 4 <= ng + 1024
+            assert 1 <= p.hint_rank <= p.kc
             st = -(-(p.sample_rows // 256) // p.sample_nsplit)
             assert -(-(p.sample_rows // 256) // st) == p.sample_nsplit
         else:

@@ -24,7 +24,7 @@ def data(nq, ng, d):
         _DATA.clear()
         g = torch.Generator(device="cuda").manual_seed(1)
         q = torch.randn(nq, d, device="cuda", generator=g); b = torch.randn(ng, d, device="cuda", generator=g)
-        _, qbf, _ = l2_normalize(q, want_f32=False, want_delta=False)
+        _, qbf, _ = l2_normalize(q, want_f32=False, want_delta=False, pad_rows_to=128)
         _, gbf, _ = l2_normalize(b, want_f32=False, want_delta=False)
         _DATA[key] = (qbf, gbf)
     return _DATA[key]
@@ -35,6 +35,7 @@ def run(nq, ng, d, kc, flags, iters=20):
     ld = qbf.shape[1]
     plan = _lib.Plan()
     _lib.check(lib.hcir_simtopk_plan(nq, ng, ld, kc, 148, plan))
+    plan.q_rows = -(-nq // 128) * 128
     ws = torch.empty(int(plan.bytes), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     call = lambda: _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, gbf.data_ptr(), ng, ld, plan, ws.data_ptr(), st))
