@@ -8,10 +8,10 @@ from .classifier import KNeighborsClassifierB200  # noqa: F401
 from .retrieval import (retrieve_similar_images, HairRetrievalB200, FlatIndex,  # noqa: F401
                         compute_similarity_topk, clear_bank_cache)
 from .sharded import ShardPlan, ShardedGallery, exchange_candidates  # noqa: F401
-from . import synth  # noqa: F401
+from . import synth, formats, metrics  # noqa: F401
 
 __all__ = [
     "GalleryBank", "knn_topk", "knn_predict", "l2_normalize", "KNeighborsClassifierB200",
     "retrieve_similar_images", "HairRetrievalB200", "FlatIndex", "compute_similarity_topk",
-    "clear_bank_cache", "ShardPlan", "ShardedGallery", "exchange_candidates", "synth",
+    "clear_bank_cache", "ShardPlan", "ShardedGallery", "exchange_candidates", "synth", "formats", "metrics",
 ]

@@ -112,12 +112,12 @@ class GalleryBank:
                  chunk_rows: int = 1 << 18):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
-        feats, _ = _as_2d_f32(features, "features")
+        lazy_numpy = isinstance(features, np.ndarray) and features.ndim == 2
+        if lazy_numpy:
+            feats = features  # (memory-mapped) numpy: converted chunk by chunk below, never copied whole
+        else:
+            feats, _ = _as_2d_f32(features, "features")
         n, d = feats.shape
-        if n < 1:
-            raise ValueError("empty gallery")
-        if n >= (1 << 31) - 256:
-            raise ValueError("a gallery shard holds fewer than 2^31 rows")
         self.n, self.d = int(n), int(d)
         self.ld = self.lib.hcir_padded_dim(d)
         self.idx_offset = int(idx_offset)
@@ -129,6 +129,8 @@ class GalleryBank:
             for a in range(0, n, chunk_rows):
                 b = min(n, a + chunk_rows)
                 x = feats[a:b]
+                if lazy_numpy:
+                    x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
                 if not x.is_cuda:
                     x = x.contiguous().to(self.device, non_blocking=True)
                 elif x.device != self.device:

@@ -376,3 +376,41 @@ def test_c2_full_size_properties():
     pred = gb.predict(qs[:2000], k)
     ref = O.vote_uniform(bl[idx[:2000]].cpu().numpy(), np.arange(61))
     np.testing.assert_array_equal(pred.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------ next rows (8f)
+def test_load_gallery_from_npy_and_shard(tmp_path):
+    from hcir_b200 import formats
+    bank, _ = synth.make_clustered(6000, 96, 7, 51)
+    qs, _ = synth.make_clustered(20, 96, 7, 52)
+    paths = [f"db/{i:05d}_hair.png" for i in range(6000)]
+    formats.save_embeddings(str(tmp_path), bank.numpy(), paths)
+    gb, p2 = formats.load_gallery(str(tmp_path), chunk_rows=1024)
+    assert p2 == paths and gb.n == 6000
+    s_ref, i_ref = GalleryBank(bank).topk(qs, 10)
+    s, i = gb.topk(qs, 10)
+    assert torch.equal(i, i_ref) and torch.equal(s, s_ref)
+    shard, _ = formats.load_gallery(str(tmp_path), rows=(2000, 5000))
+    s2, i2 = shard.topk(qs, 10)
+    assert int(i2.min()) >= 2000 and int(i2.max()) < 5000
+    recs = formats.top100_records([f"q{j}_hair.png" for j in range(20)], i.numpy(), paths)
+    assert recs[3]["top100"][0] == paths[int(i[3, 0])].split("/")[-1]
+
+
+def test_kth_neighbour_matches_neg_sampler_static():
+    """HairPretraining/src/neg_sampling.py:26-53 (cosine): k-th entry of the descending sort."""
+    from hcir_b200 import metrics
+    g = torch.Generator().manual_seed(8)
+    emb = torch.randn(256, 512, generator=g)
+    en = emb / torch.norm(emb, dim=1, keepdim=True).clamp(min=1e-8)
+    sim = torch.mm(en, en.t())
+    _, order = torch.sort(sim, dim=1, descending=True)
+    for k in (1, 7, 64):
+        ours = metrics.kth_neighbour(emb, k)
+        ref = order[:, k - 1]
+        same = ours == ref
+        # any disagreement must be a near-tie in the reference's own fp32 similarities
+        for r in torch.nonzero(~same).flatten().tolist():
+            assert abs(float(sim[r, ours[r]] - sim[r, ref[r]])) < O.TAU
+        assert same.float().mean() > 0.99
+    assert torch.equal(metrics.kth_neighbour(emb, 1), torch.arange(256))  # rank 1 is the row itself
