@@ -366,31 +366,43 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // rows are expected to exceed it (performance only; K3 verifies it and falls back if not).
 // grid nq, block 128, dynamic smem: num_chunks keys + hist + scratch.
 // ---------------------------------------------------------------------------------------------
-constexpr int kThrThreads = 128;
+constexpr int kThrWarps = 4;  // queries per CTA, one warp each: no block barriers at all
 
-__global__ void __launch_bounds__(kThrThreads)
-threshold_kernel(const float* __restrict__ cmax, int num_chunks, int kc, int hint_rank,
+// k-th largest of vals[0..n) (ordered bits, shared memory) by bitwise binary search: for each bit
+// from the top, keep it if at least k values are >= the candidate prefix.  32 warp-wide counting
+// steps, no data movement, no barriers.
+__device__ __forceinline__ uint32_t warp_kth_u32(const uint32_t* vals, int n, int k, int lane) {
+  uint32_t prefix = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
+    int c = 0;
+    for (int i = lane; i < n; i += kWarp) c += (vals[i] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(kFull, c);
+    if (c >= k) prefix = cand;
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(kThrWarps* kWarp)
+threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int kc, int hint_rank,
                  float* __restrict__ thr0, float* __restrict__ thr_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* vals = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* hist = vals + num_chunks;
-  uint32_t* scratch = hist + 256;
-  const int64_t q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * kThrWarps + warp;
+  if (q >= nq) return;  // warp-uniform
+  uint32_t* vals = reinterpret_cast<uint32_t*>(smem_raw) + static_cast<size_t>(warp) * num_chunks;
   const float* src = cmax + q * static_cast<int64_t>(num_chunks);
-  for (int i = threadIdx.x; i < num_chunks; i += kThrThreads) vals[i] = f2ord(src[i]);
-  __syncthreads();
-  if (num_chunks < kc) {
-    if (threadIdx.x == 0) {
-      thr0[q] = -INFINITY;
-      thr_hi[q] = -INFINITY;
-    }
-    return;
+  for (int i = lane; i < num_chunks; i += kWarp) vals[i] = f2ord(src[i]);
+  __syncwarp();
+  float t = -INFINITY, h = -INFINITY;
+  if (num_chunks >= kc) {
+    t = ord2f(warp_kth_u32(vals, num_chunks, kc, lane));
+    h = ord2f(warp_kth_u32(vals, num_chunks, hint_rank, lane));
   }
-  const uint32_t t = block_kth_u32(vals, num_chunks, kc, hist, scratch);
-  const uint32_t h = block_kth_u32(vals, num_chunks, hint_rank, hist, scratch);
-  if (threadIdx.x == 0) {
-    thr0[q] = ord2f(t);
-    thr_hi[q] = ord2f(h);
+  if (lane == 0) {
+    thr0[q] = t;
+    thr_hi[q] = h;
   }
 }
 
@@ -529,13 +541,14 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     rc = launch_mode<kModeSample>(mq, ms, sp, sms, st);
     if (rc != HCIR_OK) return rc;
     thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
-    const size_t smem = static_cast<size_t>(plan->num_chunks) * 4 + (256 + 8) * 4;
+    const size_t smem = static_cast<size_t>(kThrWarps) * plan->num_chunks * 4;
     HCIR_REQUIRE(smem <= 200 * 1024, "simtopk: %d sample chunks do not fit in shared memory", plan->num_chunks);
     HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     HCIR_REQUIRE(plan->hint_rank >= 1 && plan->hint_rank <= plan->kc, "simtopk: bad hint_rank=%d", plan->hint_rank);
-    threshold_kernel<<<static_cast<unsigned>(nq), kThrThreads, smem, st>>>(
-        sp.cmax, plan->num_chunks, plan->kc, plan->hint_rank, thr0, reinterpret_cast<float*>(ws + plan->thr_hi_off));
+    threshold_kernel<<<static_cast<unsigned>(ceil_div_i64(nq, kThrWarps)), kThrWarps * kWarp, smem, st>>>(
+        sp.cmax, nq, plan->num_chunks, plan->kc, plan->hint_rank, thr0,
+        reinterpret_cast<float*>(ws + plan->thr_hi_off));
     HCIR_CUDA_TRY(cudaGetLastError());
   }
 

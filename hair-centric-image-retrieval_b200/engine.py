@@ -177,6 +177,7 @@ class GalleryBank:
         if (cls_idx >= len(self.classes_)).any() or (self.classes_[np.minimum(cls_idx, len(self.classes_) - 1)] != y).any():
             raise ValueError("labels contain values missing from `classes`")
         self.labels = torch.from_numpy(cls_idx.astype(np.int32)).to(self.device)
+        self._cls_dev = None
 
     # ------------------------------------------------------------------ planning
     def choose_kc(self, k: int) -> int:
@@ -207,13 +208,21 @@ class GalleryBank:
             return _to_host(sims, kind), _to_host(idx, kind)
 
     def _topk_device(self, q: torch.Tensor, k: int, mode: str = "auto"):
+        sims, idx, _ = self._search(q, k, mode, None)
+        return sims, idx
+
+    def _search(self, q: torch.Tensor, k: int, mode: str = "auto", tail=None):
+        """Exact top-k of device queries.  ``tail(sims, idx)`` enqueues whatever consumes the
+        result (label gather, vote); it runs BEFORE the 4-byte read-back that decides whether the
+        exact fallback is needed, so the device never idles on that host round trip, and is run
+        again on the (rare) fallback.  Returns (sims, idx, tail result)."""
         lib = self.lib
         nq = q.shape[0]
         dev = self.device
         out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
         out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         if nq == 0:
-            return out_sim, out_idx
+            return out_sim, out_idx, (tail(out_sim, out_idx) if tail else None)
         if mode not in ("auto", "tensor", "exact"):
             raise ValueError(f"unknown mode {mode!r}")
         tensor = mode == "tensor" or (mode == "auto" and self.use_tensor_path(nq, k))
@@ -223,7 +232,7 @@ class GalleryBank:
         if not tensor:
             self._exact(q32, None, nq, k, out_sim, out_idx)
             self.last_stats = {"path": "exact", "uncertified": 0}
-            return out_sim, out_idx
+            return out_sim, out_idx, (tail(out_sim, out_idx) if tail else None)
         kc = self.choose_kc(k)
         plan = Plan()
         _lib.check(lib.hcir_simtopk_plan(nq, self.n, self.ld, kc, self.sm_count, plan), "simtopk_plan")
@@ -247,13 +256,15 @@ class GalleryBank:
             q32.data_ptr(), self.g32.data_ptr(), self.ld, nq, self.n, k, self.idx_offset, plan, ws.data_ptr(),
             qdl.data_ptr(), self.g_delta_max, self.eps_acc, out_sim.data_ptr(), out_idx.data_ptr(),
             unc_list.data_ptr(), unc_cnt.data_ptr(), st)), "select_rescore")
+        res = tail(out_sim, out_idx) if tail else None
         n_unc = int(unc_cnt.item())  # 4-byte readback: decides whether the exact fallback runs
         if n_unc > 0:
             self._exact(q32, unc_list, n_unc, k, out_sim, out_idx)
+            res = tail(out_sim, out_idx) if tail else None
         self.last_stats = {"path": "tensor", "uncertified": n_unc, "nsplit": int(plan.nsplit),
                            "kc": int(plan.kc), "cap": int(plan.cap), "workspace_bytes": int(plan.bytes),
                            "sample_rows": int(plan.sample_rows), "chunk_w": int(plan.chunk_w)}
-        return out_sim, out_idx
+        return out_sim, out_idx, res
 
     def _exact(self, q32, qlist, nlist, k, out_sim, out_idx):
         lib = self.lib
@@ -295,13 +306,22 @@ class GalleryBank:
                 q = q.contiguous().to(self.device, non_blocking=True)
             elif q.device != self.device:
                 q = q.to(self.device)
-            sims, idx = self._topk_device(q, int(k), mode)
-            pred_idx = self.vote(sims, self.neighbour_labels(idx), T=T)
-            cls = torch.from_numpy(self.classes_.astype(np.int64)).to(self.device)
-            pred = cls[pred_idx.long()]
+            cls = self._classes_device()
+
+            def tail(s, i):
+                return cls[self.vote(s, self.neighbour_labels(i), T=T).long()]
+
+            sims, idx, pred = self._search(q, int(k), mode, tail)
             if return_neighbors:
                 return _to_host(pred, kind), _to_host(sims, kind), _to_host(idx, kind)
             return _to_host(pred, kind)
+
+    def _classes_device(self) -> torch.Tensor:
+        if self.labels is None:
+            raise ValueError("this GalleryBank was built without labels")
+        if getattr(self, "_cls_dev", None) is None or self._cls_dev.shape[0] != len(self.classes_):
+            self._cls_dev = torch.from_numpy(np.asarray(self.classes_).astype(np.int64)).to(self.device)
+        return self._cls_dev
 
     def predict_multi_k(self, queries, ks, *, T=None, mode: str = "auto"):
         """One search at max(ks), one prefix vote per k (the reference recomputes the whole
