@@ -28,9 +28,17 @@ constexpr int kBlockM = 128;   // query rows per tile  (UMMA M, TMEM lanes)
 constexpr int kBlockN = 256;   // gallery rows per tile (UMMA N, TMEM columns)
 constexpr int kBlockK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kBBytes = kBlockN * kBlockK * 2;  // 32 KiB
+constexpr int kBBytes = kBlockN * kBlockK * 2;  // 32 KiB (per CTA: kBBytes / kCtas)
+// kCtas = 1: one CTA per 128 x 256 tile.  kCtas = 2: a CTA pair (cluster of 2, same TPC) computes a
+// 256 x 256 tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 query rows and HALF
+// of the gallery tile, which cuts the shared-memory traffic per flop by a third (the 1-CTA kernel
+// is bound by it) and leaves room for a 6-stage ring.
+template <int kCtas> struct SimCfg {
+  static constexpr int kStages = (kCtas == 2) ? 6 : 4;
+  static constexpr int kBBytesCta = kBBytes / kCtas;
+  static constexpr int kStageBytes = kABytes + kBBytesCta;
+};
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBlockN;  // 512: all of TMEM
 // Epilogue warps 0 .. 4*kColHalves-1: warp % 4 = TMEM lane quarter (32 query rows), warp / 4 =
@@ -47,12 +55,15 @@ constexpr int kSimThreads = (kNumEpiWarps + 4) * 32;
 // per-warp staging of one chunk's survivor values: [32 columns][32 lanes] x 4 bytes (column-major:
 // conflict-free for any set of active lanes); doubles as the prune scratch
 constexpr int kStageBytesPerWarp = 32 * 32 * 4;
-constexpr size_t kSimSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kStages) * (kABytes + kBBytes) +
-                                 256 /*barriers + tmem slot*/ + kNumEpiWarps * kStageBytesPerWarp;
+template <int kCtas> constexpr size_t sim_smem_bytes() {
+  return 1024 /*align slack*/ + static_cast<size_t>(SimCfg<kCtas>::kStages) * SimCfg<kCtas>::kStageBytes +
+         256 /*barriers + tmem slot*/ + kNumEpiWarps * kStageBytesPerWarp;
+}
 
 struct SimParams {
   int64_t nq, ng;
-  int ld, num_kb, num_qt, tiles_total, tiles_per_split, nsplit, cap, kc, num_items, flags;
+  int ld, num_kb, num_qt, num_qu, tiles_total, tiles_per_split, nsplit, cap, kc, num_items, flags;
+  // num_qu = query-tile units per split: num_qt (1 CTA per tile) or ceil(num_qt / 2) (CTA pairs)
   // one candidate list per (query, gallery split, column half): nlists = kColHalves * nsplit
   int32_t* counts;    // [nq][nlists]      main: candidates per list
   uint64_t* keys;     // [nq][nlists][cap] main: candidate keys (RAW, see scan_chunk)
@@ -116,24 +127,40 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, u
   __syncwarp();
 }
 
-template <int kMode>
+// Experiment knob (off by default): query-tile units that share a gallery split start their walk
+// over its tiles at different points, so concurrently running CTAs request different gallery lines.
+// Measured: no gain, slightly slower -- same-line requests from many SMs merge well in L2, there
+// is no hot-spotting to relieve.
+__device__ __forceinline__ int tile_rotation(int unit_in_split, int num_tiles, int flags) {
+  if (!(flags & HCIR_FLAG_ROTATE)) return 0;
+  return static_cast<int>((static_cast<unsigned>(unit_in_split) * 7u) % static_cast<unsigned>(num_tiles));
+}
+
+template <int kMode, int kCtas>
 __global__ void __launch_bounds__(kSimThreads, 1)
 simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                const SimParams p) {
+  constexpr int kStages = SimCfg<kCtas>::kStages;
+  constexpr int kBBytesCta = SimCfg<kCtas>::kBBytesCta;
   extern __shared__ uint8_t smem_dyn[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment; align by hand, do not trust the base.
+  // (Both CTAs of a pair see the same offset: the dynamic smem base is the same in every CTA.)
   uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * SimCfg<kCtas>::kStageBytes);
   uint64_t* full_bar = bars;                          // [kStages]   TMA -> MMA
   uint64_t* empty_bar = bars + kStages;               // [kStages]   MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * kStages;           // [kAccStages] MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kStages + kAccStages;  // [kAccStages] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages);
-  uint8_t* stage_all = smem + kStages * (kABytes + kBBytes) + 256;  // kNumEpiWarps x kStageBytesPerWarp
+  uint8_t* stage_all = smem + kStages * SimCfg<kCtas>::kStageBytes + 256;  // kNumEpiWarps x kStageBytesPerWarp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work is distributed over "units" = CTAs (kCtas = 1) or CTA pairs (kCtas = 2)
+  const uint32_t cta_rank = (kCtas == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0u);
+  const int unit = static_cast<int>(blockIdx.x) / kCtas, num_units = static_cast<int>(gridDim.x) / kCtas;
 
   if (warp == kTmaWarp && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
@@ -141,18 +168,18 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], kCtas);   // the pair's two producers both arrive on the leader's
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < kAccStages; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], kNumEpiWarps);
+      ptx::mbar_init(&tempty_bar[a], kNumEpiWarps * kCtas);  // both CTAs' epilogues release the leader
     }
     ptx::fence_mbar_init();
   }
-  if (warp == kAllocWarp) ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
+  if (warp == kAllocWarp) ptx::tmem_alloc<kCtas>(tmem_slot, kTmemCols);
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -160,20 +187,33 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int split = item / p.num_qt, qt = item - split * p.num_qt;
+      const uint64_t g_hint = (p.num_qt == 1) ? ptx::kEvictFirst : ptx::kEvictNormal;
+      for (int item = unit; item < p.num_items; item += num_units) {
+        const int split = item / p.num_qu, qt = (item - split * p.num_qu) * kCtas + static_cast<int>(cta_rank);
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
-        for (int t = t0; t < t1; ++t) {
+        const int nt = t1 - t0, rot = tile_rotation(item - split * p.num_qu, nt, p.flags);
+        for (int ti = 0; ti < nt; ++ti) {
+          const int t = t0 + (ti + rot) % nt;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
-            // queries are re-read by every gallery tile: keep them in L2; gallery streams once
-            ptx::tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * kABytes, kb * kBlockK, qt * kBlockM,
-                             ptx::kEvictLast);
-            // one query tile: every gallery byte is used exactly once -> do not keep it in L2
-            ptx::tma_load_2d(&tmap_g, &full_bar[stage], smem_b + stage * kBBytes, kb * kBlockK, t * kBlockN,
-                             p.num_qt == 1 ? ptx::kEvictFirst : ptx::kEvictNormal);
+            // queries are re-read by every gallery tile: keep them in L2.  One query tile: every
+            // gallery byte is used exactly once -> evict first.
+            if constexpr (kCtas == 1) {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+              ptx::tma_load_2d(&tmap_q, &full_bar[stage], smem_a + stage * kABytes, kb * kBlockK, qt * kBlockM,
+                               ptx::kEvictLast);
+              ptx::tma_load_2d(&tmap_g, &full_bar[stage], smem_b + stage * kBBytes, kb * kBlockK, t * kBlockN,
+                               g_hint);
+            } else {
+              // both CTAs' bytes are accounted on the LEADER's barrier
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytesCta));
+              else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+              ptx::tma_load_2d_2sm(&tmap_q, &full_bar[stage], smem_a + stage * kABytes, kb * kBlockK, qt * kBlockM,
+                                   ptx::kEvictLast);
+              ptx::tma_load_2d_2sm(&tmap_g, &full_bar[stage], smem_b + stage * kBBytesCta, kb * kBlockK,
+                                   t * kBlockN + static_cast<int>(cta_rank) * (kBlockN / 2), g_hint);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -181,11 +221,11 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, kBlockN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM * kCtas, kBlockN);
       uint32_t stage = 0, phase = 0, iter = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int split = item / p.num_qt;
+      for (int item = unit; item < p.num_items; item += num_units) {
+        const int split = item / p.num_qu;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
         for (int t = t0; t < t1; ++t, ++iter) {
@@ -197,16 +237,21 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t a_addr = ptx::smem_u32(smem_a + stage * kABytes);
-            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * kBBytes);
+            const uint32_t b_addr = ptx::smem_u32(smem_b + stage * kBBytesCta);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advancing K inside the 128-byte swizzle row = +32 bytes on the start address
               const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * kUmmaK * 2);
               const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 2);
-              ptx::umma_bf16<1>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::umma_bf16<kCtas>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            ptx::umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
-            if (kb == p.num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready
+            if constexpr (kCtas == 1) {
+              ptx::umma_commit(&empty_bar[stage]);              // smem slot free once these MMAs retire
+              if (kb == p.num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready
+            } else {  // same-offset barriers of BOTH CTAs of the pair
+              ptx::umma_commit_2sm(&empty_bar[stage], 0b11);
+              if (kb == p.num_kb - 1) ptx::umma_commit_2sm(&tfull_bar[acc], 0b11);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -221,13 +266,15 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     constexpr int kChunks = kHalfCols / 32;  // 32-column chunks per warp per tile
     if constexpr (kMode == kModeSample) {
       // ---- sample pass: maxima of chunk_w consecutive sample columns, no per-row state ----
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int split = item / p.num_qt, qt = item - split * p.num_qt;
+      for (int item = unit; item < p.num_items; item += num_units) {
+        const int split = item / p.num_qu, qt = (item - split * p.num_qu) * kCtas + static_cast<int>(cta_rank);
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
         const int64_t q = static_cast<int64_t>(qt) * kBlockM + row;
         const bool active = q < p.nq;
-        for (int t = t0; t < t1; ++t, ++iter) {
+        const int nt = t1 - t0, rot = tile_rotation(item - split * p.num_qu, nt, p.flags);
+        for (int ti = 0; ti < nt; ++ti, ++iter) {
+          const int t = t0 + (ti + rot) % nt;
           const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
           ptx::mbar_wait(&tfull_bar[acc], aphase);
           ptx::tc_fence_after();
@@ -243,7 +290,10 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (c == kChunks - 1) {
               ptx::tc_fence_before();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+              if (lane == 0) {
+                if (kCtas == 1 || leader) ptx::mbar_arrive(&tempty_bar[acc]);
+                else ptx::mbar_arrive_cluster(&tempty_bar[acc], 0);  // the MMA issuer lives in the leader CTA
+              }
             }
 #pragma unroll
             for (int g8 = 0; g8 < 4; ++g8) {
@@ -285,8 +335,8 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint32_t stage_lane = ptx::smem_u32(stage_all + warp * kStageBytesPerWarp) + lane * 4;
       const int prune_at = p.cap - 32;
       const int nlists = p.nsplit * kColHalves;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int split = item / p.num_qt, qt = item - split * p.num_qt;
+      for (int item = unit; item < p.num_items; item += num_units) {
+        const int split = item / p.num_qu, qt = (item - split * p.num_qu) * kCtas + static_cast<int>(cta_rank);
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
         const int64_t q = static_cast<int64_t>(qt) * kBlockM + row;
@@ -296,7 +346,9 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (active && !(p.flags & HCIR_FLAG_NO_EMIT)) thr = p.thr0 ? p.thr0[q] : -INFINITY;
         int cnt = 0;
         uint64_t* buf = p.keys + list * static_cast<int64_t>(p.cap);
-        for (int t = t0; t < t1; ++t, ++iter) {
+        const int nt = t1 - t0, rot = tile_rotation(item - split * p.num_qu, nt, p.flags);
+        for (int ti = 0; ti < nt; ++ti, ++iter) {
+          const int t = t0 + (ti + rot) % nt;
           const uint32_t acc = iter & 1u, aphase = (iter >> 1) & 1u;
           ptx::mbar_wait(&tfull_bar[acc], aphase);
           ptx::tc_fence_after();
@@ -312,7 +364,10 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
               // this warp's part of the accumulator stage is in registers: hand it back
               ptx::tc_fence_before();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+              if (lane == 0) {
+                if (kCtas == 1 || leader) ptx::mbar_arrive(&tempty_bar[acc]);
+                else ptx::mbar_arrive_cluster(&tempty_bar[acc], 0);  // the MMA issuer lives in the leader CTA
+              }
             }
             const uint32_t gcol0 = static_cast<uint32_t>(gbase) + c * 32;
             if (full_tile) {
@@ -354,8 +409,8 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == kAllocWarp) ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+  if constexpr (kCtas == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == kAllocWarp) ptx::tmem_dealloc<kCtas>(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -471,13 +526,28 @@ static int balanced_nsplit(int64_t num_qt, int64_t tiles, int64_t max_split, int
   return best;
 }
 
-template <int kMode>
-static int launch_mode(const CUtensorMap& mq, const CUtensorMap& mg, const SimParams& p, int sms, cudaStream_t st) {
-  const int grid = p.num_items < sms ? p.num_items : sms;
-  HCIR_CUDA_TRY(cudaFuncSetAttribute(simtopk_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(kSimSmemBytes)));
-  simtopk_kernel<kMode><<<grid, kSimThreads, kSimSmemBytes, st>>>(mq, mg, p);
-  HCIR_CUDA_TRY(cudaGetLastError());
+template <int kMode, int kCtas>
+static int launch_mode(const CUtensorMap& mq, const CUtensorMap& mg, SimParams p, int sms, cudaStream_t st) {
+  p.num_qu = (p.num_qt + kCtas - 1) / kCtas;
+  p.num_items = p.num_qu * p.nsplit;
+  const int units = sms / kCtas;
+  const int grid = (p.num_items < units ? p.num_items : units) * kCtas;
+  constexpr size_t smem = sim_smem_bytes<kCtas>();
+  HCIR_CUDA_TRY(cudaFuncSetAttribute(simtopk_kernel<kMode, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kSimThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HCIR_CUDA_TRY(cudaLaunchKernelEx(&cfg, simtopk_kernel<kMode, kCtas>, mq, mg, p));
   return HCIR_OK;
 }
 
@@ -534,11 +604,10 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     sp.tiles_per_split = static_cast<int>(ceil_div_i64(sp.tiles_total, sp.nsplit));
     HCIR_REQUIRE(static_cast<int>(ceil_div_i64(sp.tiles_total, sp.tiles_per_split)) == sp.nsplit,
                  "simtopk: plan.sample_nsplit=%d leaves an empty split", sp.nsplit);
-    sp.num_items = sp.num_qt * sp.nsplit;
     sp.cmax = reinterpret_cast<float*>(ws + plan->cmax_off);
     sp.chunk_w = plan->chunk_w;
     sp.num_chunks = plan->num_chunks;
-    rc = launch_mode<kModeSample>(mq, ms, sp, sms, st);
+    rc = launch_mode<kModeSample, 1>(mq, ms, sp, sms, st);
     if (rc != HCIR_OK) return rc;
     thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
     const size_t smem = static_cast<size_t>(kThrWarps) * plan->num_chunks * 4;
@@ -554,7 +623,9 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
 
   // ---- main pass ----------------------------------------------------------------------------
   if (!run_main) return HCIR_OK;
-  rc = make_bf16_map(&mg, g_bf16, ng, ld, ld, kBlockN);
+  // CTA pairs need two query tiles per unit; one query tile (streaming regime) stays 1-CTA
+  const bool pairs = (p.num_qt >= 2) && !(plan->flags & HCIR_FLAG_ONE_CTA);
+  rc = make_bf16_map(&mg, g_bf16, ng, ld, ld, pairs ? kBlockN / 2 : kBlockN);
   if (rc != HCIR_OK) return rc;
   p.ng = ng;
   p.tiles_total = static_cast<int>(ceil_div_i64(ng, kBlockN));
@@ -563,14 +634,15 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
                "simtopk: plan.nsplit=%d leaves an empty split for %d tiles", plan->nsplit, p.tiles_total);
   p.nsplit = plan->nsplit;
   p.cap = plan->cap;
-  p.num_items = p.num_qt * p.nsplit;
   p.counts = reinterpret_cast<int32_t*>(ws + plan->counts_off);
   p.keys = reinterpret_cast<uint64_t*>(ws + plan->keys_off);
   p.thr0 = thr0;
   p.thr_out = reinterpret_cast<float*>(ws + plan->thr_out_off);
   p.dump = dump;
   p.flags = plan->flags;
-  return dump != nullptr ? launch_mode<kModeDump>(mq, mg, p, sms, st) : launch_mode<kModeMain>(mq, mg, p, sms, st);
+  if (pairs)
+    return dump != nullptr ? launch_mode<kModeDump, 2>(mq, mg, p, sms, st) : launch_mode<kModeMain, 2>(mq, mg, p, sms, st);
+  return dump != nullptr ? launch_mode<kModeDump, 1>(mq, mg, p, sms, st) : launch_mode<kModeMain, 1>(mq, mg, p, sms, st);
 }
 
 }  // namespace hcir
@@ -585,7 +657,10 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   const int64_t tiles = ceil_div_i64(ng, kBlockN);
   *plan = hcir_plan_t{};
   plan->kc = kc;
-  plan->nsplit = balanced_nsplit(num_qt, tiles, 4 * sm_count, sm_count);
+  // the main pass runs on CTA pairs (units of two query tiles) as soon as there are two query tiles
+  const bool pairs = num_qt >= 2;
+  plan->nsplit = pairs ? balanced_nsplit((num_qt + 1) / 2, tiles, 4 * sm_count, sm_count / 2)
+                       : balanced_nsplit(num_qt, tiles, 4 * sm_count, sm_count);
 
   // sample pass: num_chunks = 2*kc chunk maxima over S = 2*kc*chunk_w strided gallery rows, as long
   // as the sample stays a small fraction of the gallery (its contraction is extra work)

@@ -41,6 +41,8 @@ extern "C" {
 #define HCIR_FLAG_NO_EMIT 1     /* main pass emits nothing: pure contraction throughput        */
 #define HCIR_FLAG_SAMPLE_ONLY 2 /* enqueue only the sample pass + threshold kernel             */
 #define HCIR_FLAG_MAIN_ONLY 4   /* enqueue only the main pass (thr0 already in the workspace)  */
+#define HCIR_FLAG_ROTATE 32     /* main pass: units start their gallery walk at staggered tiles */
+#define HCIR_FLAG_ONE_CTA 16    /* main pass: never use CTA pairs (tcgen05 cta_group::1 only)  */
 
 typedef void* hcir_stream_t; /* cudaStream_t */
 
