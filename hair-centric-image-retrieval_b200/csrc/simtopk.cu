@@ -623,8 +623,9 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
 
   // ---- main pass ----------------------------------------------------------------------------
   if (!run_main) return HCIR_OK;
-  // CTA pairs need two query tiles per unit; one query tile (streaming regime) stays 1-CTA
-  const bool pairs = (p.num_qt >= 2) && !(plan->flags & HCIR_FLAG_ONE_CTA);
+  // CTA pairs (cta_group::2) are opt-in: interleaved A/B on C2/C3/D=2048 shapes has the 1-CTA kernel
+  // 3-7 % faster under the sustained power cap (profiles/README.md)
+  const bool pairs = (p.num_qt >= 2) && (plan->flags & HCIR_FLAG_CTA_PAIRS);
   rc = make_bf16_map(&mg, g_bf16, ng, ld, ld, pairs ? kBlockN / 2 : kBlockN);
   if (rc != HCIR_OK) return rc;
   p.ng = ng;
@@ -657,8 +658,7 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   const int64_t tiles = ceil_div_i64(ng, kBlockN);
   *plan = hcir_plan_t{};
   plan->kc = kc;
-  // the main pass runs on CTA pairs (units of two query tiles) as soon as there are two query tiles
-  const bool pairs = num_qt >= 2;
+  const bool pairs = false;  // see HCIR_FLAG_CTA_PAIRS
   plan->nsplit = pairs ? balanced_nsplit((num_qt + 1) / 2, tiles, 4 * sm_count, sm_count / 2)
                        : balanced_nsplit(num_qt, tiles, 4 * sm_count, sm_count);
 

@@ -42,7 +42,7 @@ extern "C" {
 #define HCIR_FLAG_SAMPLE_ONLY 2 /* enqueue only the sample pass + threshold kernel             */
 #define HCIR_FLAG_MAIN_ONLY 4   /* enqueue only the main pass (thr0 already in the workspace)  */
 #define HCIR_FLAG_ROTATE 32     /* main pass: units start their gallery walk at staggered tiles */
-#define HCIR_FLAG_ONE_CTA 16    /* main pass: never use CTA pairs (tcgen05 cta_group::1 only)  */
+#define HCIR_FLAG_CTA_PAIRS 16  /* main pass on CTA pairs: tcgen05.mma.cta_group::2, 256x256 tile */
 
 typedef void* hcir_stream_t; /* cudaStream_t */
 

@@ -62,9 +62,10 @@ def test_l2norm_strided_and_unaligned_input():
 
 
 # ------------------------------------------------------------------------------------ K2 (raw tiles)
+@pytest.mark.parametrize("flags", [0, 16, 48])  # 1-CTA (default); CTA pairs (cta_group::2); pairs + rotation
 @pytest.mark.parametrize("nq,ng,d", [(128, 256, 64), (1, 300, 64), (130, 1000, 128), (257, 2049, 768),
                                      (64, 5000, 512), (300, 777, 2048)])
-def test_simtopk_accumulator_tiles_match_fp32_matmul(nq, ng, d):
+def test_simtopk_accumulator_tiles_match_fp32_matmul(nq, ng, d, flags):
     """The tcgen05 contraction itself: dump every accumulator value and compare with an fp32
     matmul of the same bf16 operands (bf16 products are exact in fp32; only the accumulation
     order differs)."""
@@ -78,6 +79,7 @@ def test_simtopk_accumulator_tiles_match_fp32_matmul(nq, ng, d):
     kc = 40
     plan = _lib.Plan()
     _lib.check(lib.hcir_simtopk_plan(nq, ng, ld, kc, 148, plan))
+    plan.flags = flags
     ws = torch.zeros(int(plan.bytes), dtype=torch.uint8, device="cuda")
     scores = torch.full((nq, ng), float("nan"), device="cuda")
     _lib.check(lib.hcir_simtopk_debug(qbf.data_ptr(), nq, gbf.data_ptr(), ng, ld, plan, ws.data_ptr(),

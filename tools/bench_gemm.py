@@ -72,3 +72,35 @@ if __name__ == "__main__":
             run(4096, 1000000, 768, 264, flags)
             run(64, 2000000, 768, 104, flags)
             run(16384, 200000, 2048, 464, flags)
+
+
+def ab(nq, ng, d, kc, flag_list, rounds=30):
+    """Interleaved A/B/...: one launch of each variant per round, medians over rounds (robust to the
+    slow clock drift of a power-capped part)."""
+    lib = _lib.load()
+    qbf, gbf = data(nq, ng, d)
+    ld = qbf.shape[1]
+    plans = []
+    for f in flag_list:
+        plan = _lib.Plan()
+        _lib.check(lib.hcir_simtopk_plan(nq, ng, ld, kc, 148, plan))
+        plan.q_rows = -(-nq // 128) * 128
+        plans.append(plan)
+    ws = torch.empty(int(max(p.bytes for p in plans)), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    def call(plan):
+        _lib.check(lib.hcir_simtopk(qbf.data_ptr(), nq, gbf.data_ptr(), ng, ld, plan, ws.data_ptr(), st))
+    call(plans[0])
+    for p, f in zip(plans, flag_list):
+        p.flags = f
+    times = {f: [] for f in flag_list}
+    for r in range(rounds + 3):
+        for p, f in zip(plans, flag_list):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); call(p); b.record()
+            torch.cuda.synchronize()
+            if r >= 3:
+                times[f].append(a.elapsed_time(b))
+    for f in flag_list:
+        t = np.array(times[f])
+        print(f"  flags={f:3d}: median {np.median(t):.3f} ms  min {t.min():.3f}  ({2.0*nq*ng*ld/np.median(t)/1e9:.0f} TF)", flush=True)
