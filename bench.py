@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=None, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard", default="auto", choices=["auto", "gallery", "query"],
+                    help="multi-GPU partition: gallery rows (one candidate all-gather + merge) or query replicas")
     return ap.parse_args()
 
 
@@ -203,7 +205,7 @@ def run_b200(args):
 
     import hcir_b200
     from hcir_b200 import synth
-    from hcir_b200.sharded import ShardPlan, ShardedGallery
+    from hcir_b200.sharded import QueryShardedGallery, ShardPlan, ShardedGallery, choose_sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,11 +225,19 @@ def run_b200(args):
     classes = np.arange(C)
 
     # ---- synthetic data, generated on device shard by shard (no network for datasets) ----
-    sp = ShardPlan(n, world)
-    n_local = sp.size(rank)
-    bank, bl = synth.make_clustered(n_local, d, C, 1234 + tag + 1000 * rank, device=dev)
+    shard = args.shard if args.shard != "auto" else choose_sharding(n, q, world, d=d)
+    if world == 1:
+        shard = "none"
+    sp = ShardPlan(n, world if shard == "gallery" else 1)
+    n_local = sp.size(rank if shard == "gallery" else 0)
+    # gallery sharding: every rank synthesises its own row range; query sharding: identical replicas
+    bank, bl = synth.make_clustered(n_local, d, C, 1234 + tag + (1000 * rank if shard == "gallery" else 0), device=dev)
     qs, _ = synth.make_clustered(q, d, C, 4321 + tag, device=dev)  # same queries on every rank
-    if world > 1:
+    q_local = q if shard != "query" else ShardPlan(q, world).size(rank)
+    if shard == "query":
+        gal = QueryShardedGallery(bank, bl, device=dev, classes=classes)
+        gb = gal.bank
+    elif shard == "gallery":
         gal = ShardedGallery(bank, bl, n_total=n, device=dev, classes=classes)
         gb = gal.bank
     else:
@@ -304,14 +314,14 @@ def run_b200(args):
     pk = peaks()
     roof = None
     if sim_ms:
-        flops = 2.0 * q * n_local * d  # contraction only
-        gbytes = n_local * d * 2.0 + q * d * 2.0 + q * k * 12.0  # bf16 bank once + queries + results
+        flops = 2.0 * q_local * n_local * d  # contraction only (this rank's share)
+        gbytes = n_local * d * 2.0 + q_local * d * 2.0 + q_local * k * 12.0  # bf16 bank once + queries + results
         # arithmetic intensity of the contraction = q flops per gallery byte; ridge = peak flops / peak bytes
         ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
         common = {"kernel": "simtopk_kernel<main>", "traffic": None, "kernel_ms": sim_ms,
                   "share_of_step": sim_ms / ms_per_step,
                   "other_kernels_ms": {kname: float(np.mean(v)) for kname, v in kern.items() if kname != "simtopk"}}
-        if q < ridge:
+        if q_local < ridge:
             ach = gbytes / (sim_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"],
@@ -345,7 +355,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n}x{d} gallery ({'row-sharded over %d GPUs' % world if world > 1 else '1 GPU'}), "
+            "config": {"workload": f"{args.workload}: {n}x{d} gallery ({({'gallery': 'rows sharded over %d GPUs, one candidate all-gather + merge' % world, 'query': 'replicated on %d GPUs, queries sharded, one result all-gather' % world, 'none': '1 GPU'})[shard]}), "
                                    f"{q} queries/step, k={k}, uniform vote, {C} classes",
                        "arith": "bf16 tcgen05 contraction (fp32 accumulate) + fp32 re-score of candidates",
                        "l2": f"gallery stream {n_local * gb.ld * 2 / 1e6:.0f} MB bf16 per step > 126 MB L2 (no flush needed)"

@@ -7,11 +7,12 @@ from .engine import GalleryBank, knn_topk, knn_predict, l2_normalize  # noqa: F4
 from .classifier import KNeighborsClassifierB200  # noqa: F401
 from .retrieval import (retrieve_similar_images, HairRetrievalB200, FlatIndex,  # noqa: F401
                         compute_similarity_topk, clear_bank_cache)
-from .sharded import ShardPlan, ShardedGallery, exchange_candidates  # noqa: F401
+from .sharded import (ShardPlan, ShardedGallery, QueryShardedGallery, choose_sharding,  # noqa: F401
+                      exchange_candidates)
 from . import synth, formats, metrics  # noqa: F401
 
 __all__ = [
     "GalleryBank", "knn_topk", "knn_predict", "l2_normalize", "KNeighborsClassifierB200",
     "retrieve_similar_images", "HairRetrievalB200", "FlatIndex", "compute_similarity_topk",
-    "clear_bank_cache", "ShardPlan", "ShardedGallery", "exchange_candidates", "synth", "formats", "metrics",
+    "clear_bank_cache", "ShardPlan", "ShardedGallery", "QueryShardedGallery", "choose_sharding", "exchange_candidates", "synth", "formats", "metrics",
 ]

@@ -134,3 +134,75 @@ class ShardedGallery:
             cls = torch.from_numpy(np.asarray(self.bank.classes_).astype(np.int64)).to(self.device)
             pred = cls[pred_idx.long()]
         return _to_host(pred, kind)
+
+
+def choose_sharding(n_gallery: int, n_queries: int, world: int, *, d: int = 768,
+                    replica_budget_bytes: float = 60e9) -> str:
+    """"query" or "gallery" (load balance).  A gallery that fits every GPU
+    next to its workspaces and a query batch with at least four 128-row query tiles per rank is
+    served faster by REPLICAS that split the queries (no per-rank fixed cost is repeated, the
+    only exchange is the final [Q] / [Q, k] result gather); a big gallery or a small query batch
+    (the streaming regime) is split by gallery rows."""
+    fits = n_gallery * d * 6.0 <= replica_budget_bytes      # fp32 + bf16 bank per replica
+    enough = n_queries >= world * 4 * 128
+    return "query" if (fits and enough) else "gallery"
+
+
+def gather_rows(local: torch.Tensor, sp: ShardPlan, group=None) -> torch.Tensor:
+    """ONE all-gather of per-rank row blocks of (possibly) unequal height sp.size(r) -> the
+    concatenation [sp.n, ...] on every rank (blocks are padded to the tallest for the collective)."""
+    world = dist.get_world_size(group)
+    hmax = max(sp.size(r) for r in range(world))
+    pad = torch.zeros((hmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * hmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if all(sp.size(r) == hmax for r in range(world)):
+        return out
+    return torch.cat([out[r * hmax: r * hmax + sp.size(r)] for r in range(world)], 0)
+
+
+class QueryShardedGallery:
+    """Every rank holds the whole gallery; rank r answers the contiguous query slice
+    [ShardPlan(Q, world).start(r), stop(r)) and ONE all-gather returns everybody's answers to
+    every rank.  Results are bit-identical to the single-GPU result by construction (each query is
+    answered by exactly the single-GPU code path)."""
+
+    def __init__(self, features, labels=None, *, group=None, device=None, classes=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.bank = GalleryBank(features, labels, device=device, classes=classes)
+        self.device = self.bank.device
+
+    def _slice(self, q: torch.Tensor):
+        sp = ShardPlan(int(q.shape[0]), self.world)
+        return sp, q[sp.start(self.rank):sp.stop(self.rank)]
+
+    def _gather_rows(self, local: torch.Tensor, sp: ShardPlan) -> torch.Tensor:
+        return gather_rows(local, sp, self.group)
+
+    def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
+        q, kind = _as_2d_f32(queries, "queries")
+        sp, mine = self._slice(q)
+        with torch.cuda.device(self.device):
+            if not mine.is_cuda:
+                mine = mine.contiguous().to(self.device, non_blocking=True)
+            if mine.shape[0] > 0:
+                pred = self.bank.predict(mine, int(k), T=T, mode=mode)
+            else:
+                pred = torch.empty((0,), dtype=torch.int64, device=self.device)
+            out = self._gather_rows(pred, sp)
+        return _to_host(out, kind)
+
+    def topk(self, queries, k: int, *, mode: str = "auto"):
+        q, kind = _as_2d_f32(queries, "queries")
+        sp, mine = self._slice(q)
+        with torch.cuda.device(self.device):
+            if not mine.is_cuda:
+                mine = mine.contiguous().to(self.device, non_blocking=True)
+            sims, idx = self.bank._topk_device(mine, int(k), mode)
+            o_s, o_i = self._gather_rows(sims, sp), self._gather_rows(idx, sp)
+        if kind == "torch_cuda":
+            return o_s, o_i
+        return _to_host(o_s, kind), _to_host(o_i, kind)

@@ -87,3 +87,36 @@ def test_shard_plan_offsets_cover_global_index_space():
     sp = ShardPlan(11, 4)
     assert [(sp.start(r), sp.stop(r)) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 11)]
     assert [sp.owner(i) for i in range(11)] == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3]
+
+
+def _qworker(rank, world, port, nq, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hcir_b200.sharded import gather_rows
+        sp = ShardPlan(nq, world)
+        full = torch.arange(nq * 3, dtype=torch.int64).view(nq, 3)
+        mine = full[sp.start(rank):sp.stop(rank)]          # this rank's query slice "answers"
+        out = gather_rows(mine, sp)
+        assert torch.equal(out, full)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 10), (3, 10), (3, 2)])
+def test_query_sharding_result_gather_over_gloo(world, nq):
+    """Query-replica mode: unequal (and empty) per-rank query slices come back in query order."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_qworker, args=(world, port, nq, ret), nprocs=world, join=True)
+    assert len(ret) == world
+
+
+def test_choose_sharding_policy():
+    from hcir_b200 import choose_sharding
+    assert choose_sharding(200_000, 10_000, 8) == "query"        # C2: small gallery, many queries
+    assert choose_sharding(10_000_000, 64, 8) == "gallery"       # C4: streaming regime
+    assert choose_sharding(10_000_000, 16_384, 8, d=2048) == "gallery"  # C5: replica would not fit the budget
+    assert choose_sharding(200_000, 1000, 8) == "gallery"        # too few query tiles per rank
