@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=None, help="queries in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
     ap.add_argument("--shard", default="auto", choices=["auto", "gallery", "query"],
                     help="multi-GPU partition: gallery rows (one candidate all-gather + merge) or query replicas")
     return ap.parse_args()
@@ -246,9 +247,18 @@ def run_b200(args):
     del bank
     torch.cuda.empty_cache()
 
+    # one fixed-shape step = one CUDA-graph launch (SearchSession); gallery-sharded mode runs eagerly
+    use_graph = not args.no_graph and shard in ("none", "query")
+    sess = gb.session(q, k, T=T, profile=True) if (use_graph and shard == "none") else None
+    if shard == "query" and use_graph:
+        gal.profile = True
+
     def step_resident():
+        if sess is not None:
+            pred, _, _ = sess.run(qs)
+            return pred
         if gal is not None:
-            return gal.predict(qs, k, T=T)
+            return gal.predict(qs, k, T=T, mode="auto" if use_graph or shard == "gallery" else "tensor")
         return gb.predict(qs, k, T=T)
 
     def barrier():
@@ -276,19 +286,29 @@ def run_b200(args):
         step_resident()
     barrier()
     sampler = ClockSampler(local)
-    gb.kernel_events = []
+    graph_sess = sess if sess is not None else (gal.last_session if (shard == "query" and use_graph) else None)
+    kern = {}
+    if graph_sess is None:
+        gb.kernel_events = []
     l0 = gb.launches
+
+    def timed_step():
+        out = step_resident()
+        if graph_sess is not None:  # events recorded inside the graph: read them after every replay
+            for name, ms in graph_sess.kernel_ms().items():
+                kern.setdefault(name, []).append(ms)
+        return out
+
     sampler.start()
-    total_ms = timed_loop(step_resident, args.steps, 0)
+    total_ms = timed_loop(timed_step, args.steps, 0)
     clocks = sampler.stop()
     launches = gb.launches - l0
-    events = gb.kernel_events
-    gb.kernel_events = None
+    if graph_sess is None:
+        for name, a, b in gb.kernel_events:
+            kern.setdefault(name, []).append(a.elapsed_time(b))
+        gb.kernel_events = None
     ms_per_step = total_ms / args.steps
     value = q / (ms_per_step * 1e-3)
-    kern = {}
-    for name, a, b in events:
-        kern.setdefault(name, []).append(a.elapsed_time(b))
     sim_ms = float(np.mean(kern["simtopk"])) if "simtopk" in kern else None
     stats = dict(gb.last_stats)
 
@@ -299,7 +319,8 @@ def run_b200(args):
         q_host.copy_(qs)
         torch.cuda.synchronize()
         if gal is None:
-            clf = hcir_b200.KNeighborsClassifierB200(n_neighbors=k, metric="cosine", device=dev)
+            clf = hcir_b200.KNeighborsClassifierB200(n_neighbors=k, metric="cosine", device=dev,
+                                                     use_graph=not args.no_graph)
             clf._bank = gb
             clf.classes_ = gb.classes_
             fn = lambda: clf.predict(q_host)  # noqa: E731  numpy predictions on the host

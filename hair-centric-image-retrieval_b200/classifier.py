@@ -18,7 +18,7 @@ from .engine import GalleryBank, _as_2d_f32, _to_host
 
 class KNeighborsClassifierB200:
     def __init__(self, n_neighbors: int = 5, *, metric: str = "cosine", weights: str = "uniform",
-                 T: float = 0.07, device=None, mode: str = "auto"):
+                 T: float = 0.07, device=None, mode: str = "auto", use_graph: bool = True):
         if metric != "cosine":
             raise ValueError("KNeighborsClassifierB200 implements metric='cosine' only (the reference's "
                              "only kNN metric, classification_engine.py:80)")
@@ -30,6 +30,7 @@ class KNeighborsClassifierB200:
         self.T = float(T)
         self.device = device
         self.mode = mode
+        self.use_graph = bool(use_graph)
         self._bank: GalleryBank | None = None
 
     # sklearn API -------------------------------------------------------------------------
@@ -65,6 +66,14 @@ class KNeighborsClassifierB200:
     def predict(self, X):
         self._check()
         T = self.T if self.weights == "temperature" else None
+        if self.mode == "auto" and self.use_graph:
+            # fixed shape -> the whole step is one CUDA-graph launch (captured on first use)
+            x, kind = _as_2d_f32(X, "X")
+            sess = self._bank.session(x.shape[0], self.n_neighbors, T=T) if x.shape[1] == self._bank.d else None
+            if sess is not None:
+                pred, _, _ = sess.run(x)
+                out = _to_host(pred, kind)
+                return out.numpy() if isinstance(out, torch.Tensor) and not out.is_cuda else out
         out = self._bank.predict(X, self.n_neighbors, T=T, mode=self.mode)
         return out.numpy() if isinstance(out, torch.Tensor) and not out.is_cuda else out
 

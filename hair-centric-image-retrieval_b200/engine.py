@@ -130,7 +130,7 @@ class GalleryBank:
                 b = min(n, a + chunk_rows)
                 x = feats[a:b]
                 if lazy_numpy:
-                    x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+                    x = torch.from_numpy(np.array(x, dtype=np.float32, order="C"))  # copy: memmaps are read-only
                 if not x.is_cuda:
                     x = x.contiguous().to(self.device, non_blocking=True)
                 elif x.device != self.device:
@@ -361,3 +361,141 @@ def knn_predict(query, bank, labels, k, *, T=None, mode: str = "auto"):
     if gb.labels is None:
         gb.set_labels(labels)
     return gb.predict(query, k, T=T, mode=mode)
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA-graph session: one fixed-shape predict / top-k step replayed with a single launch
+# ---------------------------------------------------------------------------------------------
+class SearchSession:
+    """A fixed-shape search step (``nq`` queries, ``k`` neighbours, optional vote) captured ONCE
+    into a CUDA graph: K1(queries) -> K2 (sample pass, thresholds, main pass) -> K3 -> label gather
+    -> K4.  ``run`` copies the queries into the static input buffer, replays the graph (one launch
+    instead of ~12 launches and their host-side allocation / planning work) and reads back the
+    4-byte count of uncertified queries; those (rare) are finished eagerly by the exact kernel.
+
+    Only the tensor path is captured; ``GalleryBank.session`` returns None when the bank would use
+    the exact CUDA-core path for this shape.  ``profile=True`` adds external CUDA events around the
+    sample pass, the main pass and K3 so their durations can be read after every replay."""
+
+    def __init__(self, bank: "GalleryBank", nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False):
+        if not (1 <= k <= bank.n):
+            raise ValueError(f"k={k} must be in [1, N={bank.n}]")
+        if vote and bank.labels is None:
+            raise ValueError("this GalleryBank was built without labels")
+        self.bank, self.nq, self.k, self.T, self.vote = bank, int(nq), int(k), T, vote
+        dev = bank.device
+        self.events = {}
+        self._profile = profile
+        with torch.cuda.device(dev):
+            self.q_in = torch.zeros((self.nq, bank.d), dtype=torch.float32, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._body(capture=False)  # warm-up: caches allocator blocks, sets func attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body(capture=True)
+        self.launches_per_run = 1 + 0  # one graph launch; the kernels inside: self.kernels_per_run
+
+    def _mark(self, name, capture):
+        if not (capture and self._profile):
+            return
+        ev = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record()
+        self.events[name] = ev
+
+    def _body(self, capture: bool):
+        b, lib, dev = self.bank, self.bank.lib, self.bank.device
+        nq, k = self.nq, self.k
+        st = _stream_ptr()
+        self.q32, self.qbf, self.qdl = l2_normalize(self.q_in, pad_rows_to=128)
+        kc = b.choose_kc(k)
+        plan = Plan()
+        _lib.check(lib.hcir_simtopk_plan(nq, b.n, b.ld, kc, b.sm_count, plan), "simtopk_plan")
+        plan.q_rows = -(-nq // 128) * 128
+        self.plan = plan
+        self.ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
+        self.out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        self.unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
+        self.unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        kernels = 1 + 1  # l2norm + the unc_cnt fill
+        self._mark("t0", capture)
+        if plan.sample_rows > 0:
+            plan.flags = 2
+            _lib.check(lib.hcir_simtopk(self.qbf.data_ptr(), nq, b.gbf.data_ptr(), b.n, b.ld, plan,
+                                        self.ws.data_ptr(), st), "simtopk(sample)")
+            self._mark("t1", capture)
+            plan.flags = 4
+            kernels += 2
+        _lib.check(lib.hcir_simtopk(self.qbf.data_ptr(), nq, b.gbf.data_ptr(), b.n, b.ld, plan,
+                                    self.ws.data_ptr(), st), "simtopk(main)")
+        plan.flags = 0
+        self._mark("t2", capture)
+        _lib.check(lib.hcir_select_rescore(self.q32.data_ptr(), b.g32.data_ptr(), b.ld, nq, b.n, k, b.idx_offset,
+                                           plan, self.ws.data_ptr(), self.qdl.data_ptr(), b.g_delta_max, b.eps_acc,
+                                           self.out_sim.data_ptr(), self.out_idx.data_ptr(),
+                                           self.unc_list.data_ptr(), self.unc_cnt.data_ptr(), st), "select_rescore")
+        self._mark("t3", capture)
+        kernels += 2
+        self.pred = self._tail() if self.vote else None
+        if self.vote:
+            kernels += 2
+        self.kernels_per_run = kernels
+
+    def _tail(self):
+        b = self.bank
+        cls = b._classes_device()
+        return cls[b.vote(self.out_sim, b.neighbour_labels(self.out_idx), T=self.T).long()]
+
+    def kernel_ms(self):
+        """Durations (ms) of the profiled phases of the LAST replay (profile=True only)."""
+        e = self.events
+        if not e:
+            return {}
+        out = {"simtopk": e["t1" if "t1" in e else "t0"].elapsed_time(e["t2"]), "select_rescore": e["t2"].elapsed_time(e["t3"])}
+        if "t1" in e:
+            out["simtopk_sample"] = e["t0"].elapsed_time(e["t1"])
+        return out
+
+    def run(self, queries):
+        """queries: [nq, d] fp32 tensor (device, or host -- pinned for an async copy).  Returns
+        (pred [nq] int64 | None, sims [nq, k], idx [nq, k]) as DEVICE tensors owned by the session
+        (valid until the next run)."""
+        b = self.bank
+        if tuple(queries.shape) != (self.nq, b.d):
+            raise ValueError(f"session was built for queries of shape {(self.nq, b.d)}, got {tuple(queries.shape)}")
+        with torch.cuda.device(b.device):
+            self.q_in.copy_(queries, non_blocking=True)
+            self.graph.replay()
+            b.launches += self.kernels_per_run
+            n_unc = int(self.unc_cnt.item())
+            pred = self.pred
+            if n_unc > 0:
+                b._exact(self.q32, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
+                if self.vote:
+                    pred = self._tail()
+            b.last_stats = {"path": "tensor+graph", "uncertified": n_unc, "nsplit": int(self.plan.nsplit),
+                            "kc": int(self.plan.kc), "cap": int(self.plan.cap),
+                            "workspace_bytes": int(self.plan.bytes), "sample_rows": int(self.plan.sample_rows),
+                            "chunk_w": int(self.plan.chunk_w)}
+        return pred, self.out_sim, self.out_idx
+
+
+def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False):
+    """Cached :class:`SearchSession` for this shape, or None if the exact path would be used."""
+    if nq < 1 or not self.use_tensor_path(nq, k):
+        return None
+    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile))
+    cache = self.__dict__.setdefault("_sessions", {})
+    s = cache.get(key)
+    if s is None:
+        if len(cache) >= 4:  # each session owns a workspace: keep a handful
+            cache.pop(next(iter(cache)))
+        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile)
+    return s
+
+
+GalleryBank.session = _bank_session

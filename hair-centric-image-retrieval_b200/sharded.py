@@ -174,6 +174,8 @@ class QueryShardedGallery:
         self.world = dist.get_world_size(group)
         self.bank = GalleryBank(features, labels, device=device, classes=classes)
         self.device = self.bank.device
+        self.profile = False       # bench.py: capture per-kernel events inside the graph
+        self.last_session = None
 
     def _slice(self, q: torch.Tensor):
         sp = ShardPlan(int(q.shape[0]), self.world)
@@ -188,7 +190,11 @@ class QueryShardedGallery:
         with torch.cuda.device(self.device):
             if not mine.is_cuda:
                 mine = mine.contiguous().to(self.device, non_blocking=True)
-            if mine.shape[0] > 0:
+            sess = self.bank.session(mine.shape[0], int(k), T=T, profile=self.profile) if mode == "auto" else None
+            if sess is not None:
+                pred, _, _ = sess.run(mine)   # the whole local step is one CUDA-graph launch
+                self.last_session = sess
+            elif mine.shape[0] > 0:
                 pred = self.bank.predict(mine, int(k), T=T, mode=mode)
             else:
                 pred = torch.empty((0,), dtype=torch.int64, device=self.device)
