@@ -449,3 +449,52 @@ def test_session_replay_equals_eager_and_handles_fallback():
     s2, i2 = dup.topk(qd, 10, mode="exact")
     assert torch.equal(idx.cpu(), i2) and torch.equal(sims.cpu(), s2)
     assert torch.equal(pred.cpu(), dup.predict(qd, 10, mode="exact"))
+
+
+def test_c3_full_size_properties():
+    """BASELINE.json configs[2] at full size (1M x 768 gallery, 4096 queries, top-100): planted rows
+    are rank 1, lists are sorted and duplicate-free, a query subsample is bit-identical on the exact
+    fp32 path, top-20 is the prefix of top-100, and an 8-way gallery sharding merges to the same result."""
+    from hcir_b200.sharded import ShardPlan, merge_topk
+    dev = "cuda"
+    n, d, q, k = 1_000_000, 768, 4096, 100
+    bank, _ = synth.make_clustered(n, d, 61, 1237, device=dev)
+    qs, _ = synth.make_clustered(q, d, 61, 4324, device=dev)
+    planted = torch.randperm(n, device=dev)[:256]
+    qs[:256] = bank[planted] * 0.3
+    gb = GalleryBank(bank)
+    sims, idx = gb.topk(qs, k)
+    assert gb.last_stats["path"] == "tensor" and gb.last_stats["uncertified"] == 0
+    assert torch.equal(idx[:256, 0], planted) and (sims[:256, 0] - 1).abs().max() < 1e-6
+    assert (sims[:, 1:] <= sims[:, :-1]).all()
+    assert all(len(torch.unique(idx[r])) == k for r in (0, 300, 4095))
+    sub = torch.arange(0, q, 257, device=dev)
+    s2, i2 = gb.topk(qs[sub], k, mode="exact")
+    assert torch.equal(i2, idx[sub]) and torch.equal(s2, sims[sub])
+    s20, i20 = gb.topk(qs, 20)
+    assert torch.equal(i20, idx[:, :20]) and torch.equal(s20, sims[:, :20])
+    sp = ShardPlan(n, 8)
+    qsub = qs[:512]
+    parts = [GalleryBank(bank[sp.start(r):sp.stop(r)], idx_offset=sp.start(r)).topk(qsub, k) for r in range(8)]
+    o_s, o_i, _ = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), None, k)
+    assert torch.equal(o_i, idx[:512]) and torch.equal(o_s, sims[:512])
+
+
+def test_c4_streaming_regime_properties():
+    """BASELINE.json configs[3] regime (small query batch against a multi-million-row gallery; 4M rows
+    here to keep the test short): every batch size 1..64 returns the planted row first and agrees
+    bit for bit with the exact fp32 path."""
+    dev = "cuda"
+    n, d, k = 4_000_000, 768, 20
+    bank, _ = synth.make_clustered(n, d, 61, 1238, device=dev)
+    gb = GalleryBank(bank)
+    del bank
+    for q in (1, 8, 64):
+        qs, _ = synth.make_clustered(q, d, 61, 4325 + q, device=dev)
+        rows = torch.randint(0, n, (q,), device=dev)
+        qs[:] = gb.g32[rows, :d] * 2.5 + 0.02 * qs      # noisy copies of gallery rows
+        sims, idx = gb.topk(qs, k)
+        assert gb.last_stats["path"] == "tensor"
+        assert torch.equal(idx[:, 0], rows)
+        s2, i2 = gb.topk(qs, k, mode="exact")
+        assert torch.equal(i2, idx) and torch.equal(s2, sims)
