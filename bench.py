@@ -248,9 +248,9 @@ def run_b200(args):
     torch.cuda.empty_cache()
 
     # one fixed-shape step = one CUDA-graph launch (SearchSession); gallery-sharded mode runs eagerly
-    use_graph = not args.no_graph and shard in ("none", "query")
+    use_graph = not args.no_graph
     sess = gb.session(q, k, T=T, profile=True) if (use_graph and shard == "none") else None
-    if shard == "query" and use_graph:
+    if gal is not None and use_graph:
         gal.profile = True
 
     def step_resident():
@@ -258,7 +258,7 @@ def run_b200(args):
             pred, _, _ = sess.run(qs)
             return pred
         if gal is not None:
-            return gal.predict(qs, k, T=T, mode="auto" if use_graph or shard == "gallery" else "tensor")
+            return gal.predict(qs, k, T=T, mode="auto" if use_graph else "tensor")
         return gb.predict(qs, k, T=T)
 
     def barrier():
@@ -286,7 +286,7 @@ def run_b200(args):
         step_resident()
     barrier()
     sampler = ClockSampler(local)
-    graph_sess = sess if sess is not None else (gal.last_session if (shard == "query" and use_graph) else None)
+    graph_sess = sess if sess is not None else (gal.last_session if (gal is not None and use_graph) else None)
     kern = {}
     if graph_sess is None:
         gb.kernel_events = []

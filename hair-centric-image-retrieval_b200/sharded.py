@@ -43,19 +43,22 @@ class ShardPlan:
 
 def exchange_candidates(sims: torch.Tensor, idx: torch.Tensor, labels: torch.Tensor | None = None,
                         group=None):
-    """The path's single collective: all-gather every rank's [Q, k] exact local top-k
-    (fp32 sims, int64 global indices, optional int32 labels) -> [G, Q, k] on every rank."""
+    """The path's single collective: ONE all-gather of every rank's [Q, k] exact local top-k
+    (fp32 sims, int64 global indices, optional int32 labels, packed into one byte buffer) ->
+    [G, Q, k] arrays on every rank."""
     world = dist.get_world_size(group)
-
-    def gather(t: torch.Tensor) -> torch.Tensor:
-        t = t.contiguous()
-        # concatenated-along-dim-0 output: the one layout both NCCL and gloo accept
-        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t, group=group)
-        return out.view((world,) + tuple(t.shape))
-
-    g_sims, g_idx = gather(sims), gather(idx)
-    g_lab = gather(labels) if labels is not None else None
+    q, k = sims.shape
+    parts = [sims.contiguous().view(torch.uint8).view(q, k * 4), idx.contiguous().view(torch.uint8).view(q, k * 8)]
+    if labels is not None:
+        parts.append(labels.contiguous().view(torch.uint8).view(q, k * 4))
+    packed = torch.cat(parts, dim=1).contiguous()                      # [Q, k*(12|16)] bytes
+    # concatenated-along-dim-0 output: the one layout both NCCL and gloo accept
+    out = torch.empty((world * q, packed.shape[1]), dtype=torch.uint8, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    out = out.view(world, q, packed.shape[1])
+    g_sims = out[:, :, : k * 4].contiguous().view(torch.float32).view(world, q, k)
+    g_idx = out[:, :, k * 4: k * 12].contiguous().view(torch.int64).view(world, q, k)
+    g_lab = out[:, :, k * 12:].contiguous().view(torch.int32).view(world, q, k) if labels is not None else None
     return g_sims, g_idx, g_lab
 
 
@@ -100,11 +103,18 @@ class ShardedGallery:
         self.bank = GalleryBank(feats, labels_local, device=device, idx_offset=self.plan.start(self.rank),
                                 classes=classes)
         self.device = self.bank.device
+        self.profile = False       # bench.py: capture per-kernel events inside the graph
+        self.last_session = None
 
     def _local(self, q: torch.Tensor, k: int, mode: str):
         """Exact local top-min(k, n_local), padded to width k with (-inf, -1)."""
         kl = min(k, self.bank.n)
-        sims, idx = self.bank._topk_device(q, kl, mode)
+        sess = self.bank.session(q.shape[0], kl, vote=False, profile=self.profile) if mode == "auto" else None
+        if sess is not None:   # the whole local step (K1..K3) is one CUDA-graph launch
+            _, sims, idx = sess.run(q)
+            self.last_session = sess
+        else:
+            sims, idx = self.bank._topk_device(q, kl, mode)
         if kl < k:
             pad_s = torch.full((q.shape[0], k - kl), float("-inf"), dtype=torch.float32, device=self.device)
             pad_i = torch.full((q.shape[0], k - kl), -1, dtype=torch.int64, device=self.device)
