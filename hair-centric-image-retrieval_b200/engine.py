@@ -183,9 +183,13 @@ class GalleryBank:
     def choose_kc(self, k: int) -> int:
         return 2 * k + 64
 
-    def use_tensor_path(self, nq: int, k: int) -> bool:
+    @staticmethod
+    def tensor_path_for(n: int, k: int) -> bool:
         # tiny galleries are not worth a tcgen05 launch: the exact CUDA-core kernel is the path
-        return self.n >= max(4096, 8 * self.choose_kc(k))
+        return n >= max(4096, 8 * (2 * k + 64))
+
+    def use_tensor_path(self, nq: int, k: int) -> bool:
+        return self.tensor_path_for(self.n, k)
 
     # ------------------------------------------------------------------ search
     def topk(self, queries, k: int, *, mode: str = "auto", return_device: bool = False):
@@ -377,12 +381,16 @@ class SearchSession:
     the exact CUDA-core path for this shape.  ``profile=True`` adds external CUDA events around the
     sample pass, the main pass and K3 so their durations can be read after every replay."""
 
-    def __init__(self, bank: "GalleryBank", nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False):
+    def __init__(self, bank: "GalleryBank", nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False,
+                 pack: bool = False):
         if not (1 <= k <= bank.n):
             raise ValueError(f"k={k} must be in [1, N={bank.n}]")
         if vote and bank.labels is None:
             raise ValueError("this GalleryBank was built without labels")
         self.bank, self.nq, self.k, self.T, self.vote = bank, int(nq), int(k), T, vote
+        # pack: results live in ONE byte block [idx | sims | labels] (hcir_packed_block_bytes), the
+        # unit of the multi-GPU candidate all-gather; out_sim / out_idx / out_lab are views of it
+        self.pack_results = bool(pack)
         dev = bank.device
         self.events = {}
         self._profile = profile
@@ -417,8 +425,19 @@ class SearchSession:
         plan.q_rows = -(-nq // 128) * 128
         self.plan = plan
         self.ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
-        self.out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        self.out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        self.out_lab = None
+        if self.pack_results:
+            with_lab = b.labels is not None
+            e = nq * k
+            self.pack = torch.zeros((int(lib.hcir_packed_block_bytes(nq, k, int(with_lab))),), dtype=torch.uint8,
+                                    device=dev)
+            self.out_idx = self.pack[: e * 8].view(torch.int64).view(nq, k)
+            self.out_sim = self.pack[e * 8: e * 12].view(torch.float32).view(nq, k)
+            if with_lab:
+                self.out_lab = self.pack[e * 12: e * 16].view(torch.int32).view(nq, k)
+        else:
+            self.out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            self.out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         self.unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
         self.unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
         kernels = 1 + 1  # l2norm + the unc_cnt fill
@@ -443,7 +462,16 @@ class SearchSession:
         self.pred = self._tail() if self.vote else None
         if self.vote:
             kernels += 2
+        if self.out_lab is not None:
+            self._gather_packed_labels()
+            kernels += 1
         self.kernels_per_run = kernels
+
+    def _gather_packed_labels(self):
+        b = self.bank
+        b.launches += 1
+        _lib.check(b.lib.hcir_gather_labels(self.out_idx.data_ptr(), self.out_idx.numel(), b.labels.data_ptr(), b.n,
+                                            b.idx_offset, self.out_lab.data_ptr(), _stream_ptr()), "gather_labels")
 
     def _tail(self):
         b = self.bank
@@ -477,6 +505,8 @@ class SearchSession:
                 b._exact(self.q32, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
                 if self.vote:
                     pred = self._tail()
+                if self.out_lab is not None:
+                    self._gather_packed_labels()
             b.last_stats = {"path": "tensor+graph", "uncertified": n_unc, "nsplit": int(self.plan.nsplit),
                             "kc": int(self.plan.kc), "cap": int(self.plan.cap),
                             "workspace_bytes": int(self.plan.bytes), "sample_rows": int(self.plan.sample_rows),
@@ -484,17 +514,17 @@ class SearchSession:
         return pred, self.out_sim, self.out_idx
 
 
-def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False):
+def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False, pack: bool = False):
     """Cached :class:`SearchSession` for this shape, or None if the exact path would be used."""
     if nq < 1 or not self.use_tensor_path(nq, k):
         return None
-    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile))
+    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile), bool(pack))
     cache = self.__dict__.setdefault("_sessions", {})
     s = cache.get(key)
     if s is None:
         if len(cache) >= 4:  # each session owns a workspace: keep a handful
             cache.pop(next(iter(cache)))
-        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile)
+        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack)
     return s
 
 

@@ -121,11 +121,44 @@ class ShardedGallery:
             sims, idx = torch.cat([sims, pad_s], 1), torch.cat([idx, pad_i], 1)
         return sims, idx
 
+    def _topk_packed(self, q: torch.Tensor, k: int, with_labels: bool):
+        """Fast path: the local step is one graph launch whose results already sit in the packed
+        block; ONE all-gather of that block; K5 reads the gathered blocks in place."""
+        sess = self.bank.session(q.shape[0], k, vote=False, profile=self.profile, pack=True)
+        if sess is None or (with_labels and sess.out_lab is None):
+            return None
+        sess.run(q)
+        self.last_session = sess
+        lib = self.bank.lib
+        has_lab = sess.out_lab is not None
+        gathered = torch.empty((self.world * sess.pack.numel(),), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(gathered, sess.pack, group=self.group)
+        nq = q.shape[0]
+        o_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        o_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        o_l = torch.empty((nq, k), dtype=torch.int32, device=self.device) if has_lab else None
+        self.bank.launches += 1
+        _lib.check(lib.hcir_merge_topk_packed(gathered.data_ptr(), self.world, nq, k, int(has_lab), o_s.data_ptr(),
+                                              o_i.data_ptr(), o_l.data_ptr() if has_lab else None, _stream_ptr()),
+                   "merge_topk_packed")
+        return o_s, o_i, o_l
+
     def topk(self, queries, k: int, *, mode: str = "auto", with_labels: bool = False):
         q, kind = _as_2d_f32(queries, "queries")
         with torch.cuda.device(self.device):
             if not q.is_cuda:
                 q = q.contiguous().to(self.device, non_blocking=True)
+            # every rank must take the same branch: the plan (not the data) decides
+            packed_ok = mode == "auto" and q.shape[0] > 0 and all(
+                GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world))
+            fast = self._topk_packed(q, int(k), with_labels) if packed_ok else None
+            if fast is not None:
+                o_s, o_i, o_l = fast
+                if with_labels:
+                    return o_s, o_i, o_l
+                if kind == "torch_cuda":
+                    return o_s, o_i
+                return _to_host(o_s, kind), _to_host(o_i, kind)
             sims, idx = self._local(q, int(k), mode)
             lab = self.bank.neighbour_labels(idx) if with_labels else None
             g_s, g_i, g_l = exchange_candidates(sims, idx, lab, self.group)

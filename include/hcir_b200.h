@@ -170,6 +170,14 @@ int hcir_merge_topk(const float* gathered_sim, const int64_t* gathered_idx,
                     const int32_t* gathered_lab, int G, int64_t nq, int k, float* out_sim,
                     int64_t* out_idx, int32_t* out_lab, hcir_stream_t stream);
 
+/* K5, packed form: `gathered` is what ONE all-gather of every rank's packed result block produces,
+ * G blocks of hcir_packed_block_bytes(nq, k, with_labels) bytes, each laid out as
+ *   int64 idx[nq][k] | float sims[nq][k] | int32 labels[nq][k] (if with_labels)
+ * and read in place (no unpacking pass). */
+size_t hcir_packed_block_bytes(int64_t nq, int k, int with_labels);
+int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int with_labels,
+                           float* out_sim, int64_t* out_idx, int32_t* out_lab, hcir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

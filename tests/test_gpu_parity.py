@@ -498,3 +498,34 @@ def test_c4_streaming_regime_properties():
         assert torch.equal(idx[:, 0], rows)
         s2, i2 = gb.topk(qs, k, mode="exact")
         assert torch.equal(i2, idx) and torch.equal(s2, sims)
+
+
+def test_packed_merge_reads_gathered_blocks_in_place():
+    """hcir_merge_topk_packed on G emulated rank blocks [idx | sims | labels] == the dense merge."""
+    from hcir_b200.sharded import ShardPlan, merge_topk
+    lib = _lib.load()
+    n, d, k, G, nq = 40000, 256, 20, 4, 130
+    bank, bl = synth.make_clustered(n, d, 9, 81)
+    qs, _ = synth.make_clustered(nq, d, 9, 82)
+    sp = ShardPlan(n, G)
+    blocks, dense = [], []
+    for r in range(G):
+        sh = GalleryBank(bank[sp.start(r):sp.stop(r)], bl[sp.start(r):sp.stop(r)], idx_offset=sp.start(r),
+                         classes=np.arange(9))
+        sess = sh.session(nq, k, vote=False, pack=True)
+        _, s, i = sess.run(qs.cuda())
+        assert sess.pack.numel() == lib.hcir_packed_block_bytes(nq, k, 1)
+        assert torch.equal(sess.out_lab, sh.neighbour_labels(i))
+        blocks.append(sess.pack.clone())
+        dense.append((s.clone(), i.clone(), sess.out_lab.clone()))
+    gathered = torch.cat(blocks)
+    o_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    o_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    o_l = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    _lib.check(lib.hcir_merge_topk_packed(gathered.data_ptr(), G, nq, k, 1, o_s.data_ptr(), o_i.data_ptr(),
+                                          o_l.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    d_s, d_i, d_l = merge_topk(torch.stack([x[0] for x in dense]), torch.stack([x[1] for x in dense]),
+                               torch.stack([x[2] for x in dense]), k)
+    assert torch.equal(o_i, d_i) and torch.equal(o_s, d_s) and torch.equal(o_l, d_l)
+    s_ref, i_ref = GalleryBank(bank).topk(qs, k, return_device=True)
+    assert torch.equal(o_i, i_ref) and torch.equal(o_s, s_ref)
