@@ -421,41 +421,73 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 // rows are expected to exceed it (performance only; K3 verifies it and falls back if not).
 // grid nq, block 128, dynamic smem: num_chunks keys + hist + scratch.
 // ---------------------------------------------------------------------------------------------
-constexpr int kThrWarps = 4;  // queries per CTA, one warp each: no block barriers at all
+constexpr int kThrWarps = 4;       // many queries: one warp per query, 4 per CTA, no block barriers
+constexpr int kThrBlockThreads = 256;  // few queries: one CTA per query (the search is latency-bound)
 
 // k-th largest of vals[0..n) (ordered bits, shared memory) by bitwise binary search: for each bit
-// from the top, keep it if at least k values are >= the candidate prefix.  32 warp-wide counting
-// steps, no data movement, no barriers.
-__device__ __forceinline__ uint32_t warp_kth_u32(const uint32_t* vals, int n, int k, int lane) {
-  uint32_t prefix = 0u;
+// below the common prefix of all values, keep it if at least k values are >= the candidate.
+// <= 32 counting steps, no data movement.  kBlock: the whole CTA cooperates (two barriers per
+// step), else one warp.
+template <bool kBlock>
+__device__ __forceinline__ uint32_t kth_u32(const uint32_t* vals, int n, int k, uint32_t* red) {
+  const int tid = kBlock ? threadIdx.x : (threadIdx.x & 31);
+  const int nthr = kBlock ? kThrBlockThreads : kWarp;
+  const int lane = threadIdx.x & 31;
+  // bits above the highest differing bit are common to every value: start below them
+  uint32_t diff = 0u;
+  const uint32_t v0 = vals[0];
+  for (int i = tid; i < n; i += nthr) diff |= vals[i] ^ v0;
+  diff = __reduce_or_sync(kFull, diff);
+  if (kBlock) {
+    if (threadIdx.x == 0) red[0] = 0u;
+    __syncthreads();
+    if (lane == 0) atomicOr(&red[0], diff);
+    __syncthreads();
+    diff = red[0];
+    __syncthreads();
+  }
+  if (diff == 0u) return v0;
+  const int hb = 31 - __clz(diff);
+  uint32_t prefix = (hb == 31) ? 0u : (v0 & ~((2u << hb) - 1u));
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
+  for (int bit = hb; bit >= 0; --bit) {
     const uint32_t cand = prefix | (1u << bit);
     int c = 0;
-    for (int i = lane; i < n; i += kWarp) c += (vals[i] >= cand) ? 1 : 0;
+    for (int i = tid; i < n; i += nthr) c += (vals[i] >= cand) ? 1 : 0;
     c = __reduce_add_sync(kFull, c);
+    if (kBlock) {
+      if (threadIdx.x == 0) red[1] = 0u;
+      __syncthreads();
+      if (lane == 0) atomicAdd(&red[1], static_cast<uint32_t>(c));
+      __syncthreads();
+      c = static_cast<int>(red[1]);
+      __syncthreads();
+    }
     if (c >= k) prefix = cand;
   }
   return prefix;
 }
 
-__global__ void __launch_bounds__(kThrWarps* kWarp)
+template <bool kBlock>
+__global__ void __launch_bounds__(kBlock ? kThrBlockThreads : kThrWarps * kWarp)
 threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int kc, int hint_rank,
                  float* __restrict__ thr0, float* __restrict__ thr_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * kThrWarps + warp;
-  if (q >= nq) return;  // warp-uniform
-  uint32_t* vals = reinterpret_cast<uint32_t*>(smem_raw) + static_cast<size_t>(warp) * num_chunks;
+  const int64_t q = kBlock ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kThrWarps + warp;
+  if (q >= nq) return;  // warp-uniform (block-uniform for kBlock)
+  uint32_t* red = reinterpret_cast<uint32_t*>(smem_raw);  // [4] block-reduction scratch
+  uint32_t* vals = red + 4 + (kBlock ? 0 : static_cast<size_t>(warp) * num_chunks);
   const float* src = cmax + q * static_cast<int64_t>(num_chunks);
-  for (int i = lane; i < num_chunks; i += kWarp) vals[i] = f2ord(src[i]);
-  __syncwarp();
+  const int tid = kBlock ? threadIdx.x : lane, nthr = kBlock ? kThrBlockThreads : kWarp;
+  for (int i = tid; i < num_chunks; i += nthr) vals[i] = f2ord(src[i]);
+  if (kBlock) __syncthreads(); else __syncwarp();
   float t = -INFINITY, h = -INFINITY;
   if (num_chunks >= kc) {
-    t = ord2f(warp_kth_u32(vals, num_chunks, kc, lane));
-    h = ord2f(warp_kth_u32(vals, num_chunks, hint_rank, lane));
+    t = ord2f(kth_u32<kBlock>(vals, num_chunks, kc, red));
+    h = ord2f(kth_u32<kBlock>(vals, num_chunks, hint_rank, red));
   }
-  if (lane == 0) {
+  if (tid == 0) {
     thr0[q] = t;
     thr_hi[q] = h;
   }
@@ -610,14 +642,22 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     rc = launch_mode<kModeSample, 1>(mq, ms, sp, sms, st);
     if (rc != HCIR_OK) return rc;
     thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
-    const size_t smem = static_cast<size_t>(kThrWarps) * plan->num_chunks * 4;
-    HCIR_REQUIRE(smem <= 200 * 1024, "simtopk: %d sample chunks do not fit in shared memory", plan->num_chunks);
-    HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
     HCIR_REQUIRE(plan->hint_rank >= 1 && plan->hint_rank <= plan->kc, "simtopk: bad hint_rank=%d", plan->hint_rank);
-    threshold_kernel<<<static_cast<unsigned>(ceil_div_i64(nq, kThrWarps)), kThrWarps * kWarp, smem, st>>>(
-        sp.cmax, nq, plan->num_chunks, plan->kc, plan->hint_rank, thr0,
-        reinterpret_cast<float*>(ws + plan->thr_hi_off));
+    float* thr_hi = reinterpret_cast<float*>(ws + plan->thr_hi_off);
+    const bool per_block = nq <= 1024;  // few queries: a CTA per query hides the search latency
+    const size_t smem = 16 + static_cast<size_t>(per_block ? 1 : kThrWarps) * plan->num_chunks * 4;
+    HCIR_REQUIRE(smem <= 200 * 1024, "simtopk: %d sample chunks do not fit in shared memory", plan->num_chunks);
+    if (per_block) {
+      HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      threshold_kernel<true><<<static_cast<unsigned>(nq), kThrBlockThreads, smem, st>>>(
+          sp.cmax, nq, plan->num_chunks, plan->kc, plan->hint_rank, thr0, thr_hi);
+    } else {
+      HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      threshold_kernel<false><<<static_cast<unsigned>(ceil_div_i64(nq, kThrWarps)), kThrWarps * kWarp, smem, st>>>(
+          sp.cmax, nq, plan->num_chunks, plan->kc, plan->hint_rank, thr0, thr_hi);
+    }
     HCIR_CUDA_TRY(cudaGetLastError());
   }
 
