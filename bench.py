@@ -386,11 +386,21 @@ def run_b200(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # captured NCCL work keeps the communicator busy at teardown (destroy_process_group was
+        # observed to hang with live CUDA graphs): drop the graphs, drain, and leave without it
+        gb.__dict__.pop("_sessions", None)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
     args = parse()
+    if os.environ.get("HCIR_DEBUG_HANG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["HCIR_DEBUG_HANG"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -50,7 +50,7 @@ SIGNATURES = {
     "hcir_vote": (_INT, [_P, _P, _I64, _INT, _INT, _F, _P, _P, _P]),
     "hcir_merge_topk": (_INT, [_P, _P, _P, _INT, _I64, _INT, _P, _P, _P, _P]),
     "hcir_packed_block_bytes": (C.c_size_t, [_I64, _INT, _INT]),
-    "hcir_merge_topk_packed": (_INT, [_P, _INT, _I64, _INT, _INT, _P, _P, _P, _P]),
+    "hcir_merge_topk_packed": (_INT, [_P, _INT, _I64, _INT, _INT, C.c_size_t, _P, _P, _P, _P]),
 }
 
 _lib = None

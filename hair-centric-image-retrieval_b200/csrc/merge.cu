@@ -88,11 +88,15 @@ extern "C" size_t hcir_packed_block_bytes(int64_t nq, int k, int with_labels) {
 }
 
 extern "C" int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int with_labels,
-                                      float* out_sim, int64_t* out_idx, int32_t* out_lab, hcir_stream_t stream) {
+                                      size_t rank_stride_bytes, float* out_sim, int64_t* out_idx, int32_t* out_lab,
+                                      hcir_stream_t stream) {
   using namespace hcir;
   HCIR_REQUIRE(gathered != nullptr || nq == 0, "merge_topk_packed: null pointer");
   const size_t e = static_cast<size_t>(nq > 0 ? nq : 0) * static_cast<size_t>(k > 0 ? k : 0);
-  const size_t block = hcir_packed_block_bytes(nq, k, with_labels);
+  const size_t min_block = hcir_packed_block_bytes(nq, k, with_labels);
+  const size_t block = rank_stride_bytes ? rank_stride_bytes : min_block;
+  HCIR_REQUIRE(block >= min_block && block % 8 == 0, "merge_topk_packed: rank stride %zu < block %zu or misaligned",
+               block, min_block);
   const char* base = static_cast<const char*>(gathered);
   // block layout: idx (8-byte aligned first) | sims | labels
   return merge_launch(base + e * 8, base, with_labels ? base + e * 12 : nullptr, block, block, block, G, nq, k,

@@ -382,7 +382,7 @@ class SearchSession:
     sample pass, the main pass and K3 so their durations can be read after every replay."""
 
     def __init__(self, bank: "GalleryBank", nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False,
-                 pack: bool = False):
+                 pack: bool = False, post=None):
         if not (1 <= k <= bank.n):
             raise ValueError(f"k={k} must be in [1, N={bank.n}]")
         if vote and bank.labels is None:
@@ -391,6 +391,11 @@ class SearchSession:
         # pack: results live in ONE byte block [idx | sims | labels] (hcir_packed_block_bytes), the
         # unit of the multi-GPU candidate all-gather; out_sim / out_idx / out_lab are views of it
         self.pack_results = bool(pack)
+        # post(session): extra work captured at the end of the graph (multi-GPU: the candidate
+        # all-gather + merge + vote).  With it the packed block gets a 16-byte trailer holding this
+        # rank's uncertified count, and run(check=False) leaves the read-back to the caller.
+        self.post, self.post_out = post, None
+        self.trailer = 16 if (pack and post is not None) else 0
         dev = bank.device
         self.events = {}
         self._profile = profile
@@ -403,7 +408,10 @@ class SearchSession:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # a captured collective: NCCL's watchdog thread polls CUDA events while we capture, which
+            # only the thread-local capture mode tolerates
+            mode = "thread_local" if post is not None else "global"
+            with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self._body(capture=True)
         self.launches_per_run = 1 + 0  # one graph launch; the kernels inside: self.kernels_per_run
 
@@ -429,8 +437,8 @@ class SearchSession:
         if self.pack_results:
             with_lab = b.labels is not None
             e = nq * k
-            self.pack = torch.zeros((int(lib.hcir_packed_block_bytes(nq, k, int(with_lab))),), dtype=torch.uint8,
-                                    device=dev)
+            self.block_bytes = int(lib.hcir_packed_block_bytes(nq, k, int(with_lab)))
+            self.pack = torch.zeros((self.block_bytes + self.trailer,), dtype=torch.uint8, device=dev)
             self.out_idx = self.pack[: e * 8].view(torch.int64).view(nq, k)
             self.out_sim = self.pack[e * 8: e * 12].view(torch.float32).view(nq, k)
             if with_lab:
@@ -465,6 +473,10 @@ class SearchSession:
         if self.out_lab is not None:
             self._gather_packed_labels()
             kernels += 1
+        if self.trailer:
+            self.pack[self.block_bytes: self.block_bytes + 4].view(torch.int32).copy_(self.unc_cnt)
+        if self.post is not None:
+            self.post_out = self.post(self)
         self.kernels_per_run = kernels
 
     def _gather_packed_labels(self):
@@ -488,10 +500,18 @@ class SearchSession:
             out["simtopk_sample"] = e["t0"].elapsed_time(e["t1"])
         return out
 
-    def run(self, queries):
+    def finish_uncertified(self, n_unc: int):
+        """Eager completion of the (rare) queries the tensor path could not certify."""
+        b = self.bank
+        b._exact(self.q32, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
+        if self.out_lab is not None:
+            self._gather_packed_labels()
+
+    def run(self, queries, check: bool = True):
         """queries: [nq, d] fp32 tensor (device, or host -- pinned for an async copy).  Returns
         (pred [nq] int64 | None, sims [nq, k], idx [nq, k]) as DEVICE tensors owned by the session
-        (valid until the next run)."""
+        (valid until the next run).  ``check=False``: only replay; the caller reads the uncertified
+        count (multi-GPU: from the gathered trailers) and calls ``finish_uncertified``."""
         b = self.bank
         if tuple(queries.shape) != (self.nq, b.d):
             raise ValueError(f"session was built for queries of shape {(self.nq, b.d)}, got {tuple(queries.shape)}")
@@ -499,6 +519,8 @@ class SearchSession:
             self.q_in.copy_(queries, non_blocking=True)
             self.graph.replay()
             b.launches += self.kernels_per_run
+            if not check:
+                return self.pred, self.out_sim, self.out_idx
             n_unc = int(self.unc_cnt.item())
             pred = self.pred
             if n_unc > 0:
@@ -514,17 +536,18 @@ class SearchSession:
         return pred, self.out_sim, self.out_idx
 
 
-def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False, pack: bool = False):
+def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False, pack: bool = False,
+                  post=None, post_key=None):
     """Cached :class:`SearchSession` for this shape, or None if the exact path would be used."""
     if nq < 1 or not self.use_tensor_path(nq, k):
         return None
-    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile), bool(pack))
+    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile), bool(pack), post_key)
     cache = self.__dict__.setdefault("_sessions", {})
     s = cache.get(key)
     if s is None:
         if len(cache) >= 4:  # each session owns a workspace: keep a handful
             cache.pop(next(iter(cache)))
-        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack)
+        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack, post=post)
     return s
 
 

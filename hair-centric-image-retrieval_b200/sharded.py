@@ -121,27 +121,52 @@ class ShardedGallery:
             sims, idx = torch.cat([sims, pad_s], 1), torch.cat([idx, pad_i], 1)
         return sims, idx
 
-    def _topk_packed(self, q: torch.Tensor, k: int, with_labels: bool):
-        """Fast path: the local step is one graph launch whose results already sit in the packed
-        block; ONE all-gather of that block; K5 reads the gathered blocks in place."""
-        sess = self.bank.session(q.shape[0], k, vote=False, profile=self.profile, pack=True)
-        if sess is None or (with_labels and sess.out_lab is None):
-            return None
-        sess.run(q)
-        self.last_session = sess
-        lib = self.bank.lib
+    def _post(self, sess, want_vote: bool, T):
+        """Tail of the step, captured into the same CUDA graph as the local search: ONE all-gather
+        of every rank's packed block (+ trailer = its uncertified count), K5 reading the gathered
+        blocks in place, and (predict) the vote."""
+        lib, dev = self.bank.lib, self.device
+        nq, k = sess.nq, sess.k
         has_lab = sess.out_lab is not None
-        gathered = torch.empty((self.world * sess.pack.numel(),), dtype=torch.uint8, device=self.device)
+        stride = sess.pack.numel()
+        gathered = torch.empty((self.world * stride,), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, sess.pack, group=self.group)
-        nq = q.shape[0]
-        o_s = torch.empty((nq, k), dtype=torch.float32, device=self.device)
-        o_i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
-        o_l = torch.empty((nq, k), dtype=torch.int32, device=self.device) if has_lab else None
+        o_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        o_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        o_l = torch.empty((nq, k), dtype=torch.int32, device=dev) if has_lab else None
         self.bank.launches += 1
-        _lib.check(lib.hcir_merge_topk_packed(gathered.data_ptr(), self.world, nq, k, int(has_lab), o_s.data_ptr(),
-                                              o_i.data_ptr(), o_l.data_ptr() if has_lab else None, _stream_ptr()),
-                   "merge_topk_packed")
-        return o_s, o_i, o_l
+        _lib.check(lib.hcir_merge_topk_packed(gathered.data_ptr(), self.world, nq, k, int(has_lab), stride,
+                                              o_s.data_ptr(), o_i.data_ptr(), o_l.data_ptr() if has_lab else None,
+                                              _stream_ptr()), "merge_topk_packed")
+        pred = None
+        if want_vote:
+            pred = self.bank._classes_device()[self.bank.vote(o_s, o_l, T=T).long()]
+        return {"gathered": gathered, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
+
+    def _step_packed(self, q: torch.Tensor, k: int, want_vote: bool, T):
+        """Whole multi-GPU step as ONE graph launch per rank; None if the tensor path does not apply."""
+        key = ("gallery-sharded", want_vote, None if T is None else float(T))
+        sess = self.bank.session(q.shape[0], k, vote=False, profile=self.profile, pack=True,
+                                 post=lambda s_: self._post(s_, want_vote, T), post_key=key)
+        if sess is None or (want_vote and sess.out_lab is None):
+            return None
+        sess.run(q, check=False)
+        self.last_session = sess
+        out = sess.post_out
+        # every rank sees every rank's uncertified count in the gathered trailers: the (rare) exact
+        # completion and the repeated exchange are taken by ALL ranks or by none
+        stride = sess.pack.numel()
+        counts = out["gathered"].view(self.world, stride)[:, sess.block_bytes: sess.block_bytes + 4].contiguous()
+        counts = counts.view(torch.int32).view(-1).tolist()
+        if any(c > 0 for c in counts):
+            if counts[self.rank] > 0:
+                sess.finish_uncertified(counts[self.rank])
+            out = self._post(sess, want_vote, T)
+        self.bank.last_stats = {"path": "tensor+graph", "uncertified": int(sum(counts)),
+                                "nsplit": int(sess.plan.nsplit), "kc": int(sess.plan.kc), "cap": int(sess.plan.cap),
+                                "workspace_bytes": int(sess.plan.bytes), "sample_rows": int(sess.plan.sample_rows),
+                                "chunk_w": int(sess.plan.chunk_w)}
+        return out
 
     def topk(self, queries, k: int, *, mode: str = "auto", with_labels: bool = False):
         q, kind = _as_2d_f32(queries, "queries")
@@ -151,9 +176,9 @@ class ShardedGallery:
             # every rank must take the same branch: the plan (not the data) decides
             packed_ok = mode == "auto" and q.shape[0] > 0 and all(
                 GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world))
-            fast = self._topk_packed(q, int(k), with_labels) if packed_ok else None
-            if fast is not None:
-                o_s, o_i, o_l = fast
+            fast = self._step_packed(q, int(k), False, None) if packed_ok else None
+            if fast is not None and (fast["lab"] is not None or not with_labels):
+                o_s, o_i, o_l = fast["sims"], fast["idx"], fast["lab"]
                 if with_labels:
                     return o_s, o_i, o_l
                 if kind == "torch_cuda":
@@ -170,7 +195,16 @@ class ShardedGallery:
         return _to_host(o_s, kind), _to_host(o_i, kind)
 
     def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
-        _, kind = _as_2d_f32(queries, "queries")
+        q, kind = _as_2d_f32(queries, "queries")
+        packed_ok = mode == "auto" and q.shape[0] > 0 and self.bank.labels is not None and all(
+            GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world))
+        if packed_ok:
+            with torch.cuda.device(self.device):
+                if not q.is_cuda:
+                    q = q.contiguous().to(self.device, non_blocking=True)
+                out = self._step_packed(q, int(k), True, T)
+            if out is not None:
+                return _to_host(out["pred"], kind)
         o_s, o_i, o_l = self.topk(queries, k, mode=mode, with_labels=True)
         with torch.cuda.device(self.device):
             pred_idx = self.bank.vote(o_s, o_l, T=T)

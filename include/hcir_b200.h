@@ -173,10 +173,13 @@ int hcir_merge_topk(const float* gathered_sim, const int64_t* gathered_idx,
 /* K5, packed form: `gathered` is what ONE all-gather of every rank's packed result block produces,
  * G blocks of hcir_packed_block_bytes(nq, k, with_labels) bytes, each laid out as
  *   int64 idx[nq][k] | float sims[nq][k] | int32 labels[nq][k] (if with_labels)
- * and read in place (no unpacking pass). */
+ * and read in place (no unpacking pass).  rank_stride_bytes = distance between two ranks' blocks
+ * (0 = exactly the block size; larger when every rank appends private trailer bytes, e.g. its
+ * count of uncertified queries). */
 size_t hcir_packed_block_bytes(int64_t nq, int k, int with_labels);
 int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int with_labels,
-                           float* out_sim, int64_t* out_idx, int32_t* out_lab, hcir_stream_t stream);
+                           size_t rank_stride_bytes, float* out_sim, int64_t* out_idx, int32_t* out_lab,
+                           hcir_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -522,7 +522,7 @@ def test_packed_merge_reads_gathered_blocks_in_place():
     o_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     o_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     o_l = torch.empty((nq, k), dtype=torch.int32, device="cuda")
-    _lib.check(lib.hcir_merge_topk_packed(gathered.data_ptr(), G, nq, k, 1, o_s.data_ptr(), o_i.data_ptr(),
+    _lib.check(lib.hcir_merge_topk_packed(gathered.data_ptr(), G, nq, k, 1, 0, o_s.data_ptr(), o_i.data_ptr(),
                                           o_l.data_ptr(), torch.cuda.current_stream().cuda_stream))
     d_s, d_i, d_l = merge_topk(torch.stack([x[0] for x in dense]), torch.stack([x[1] for x in dense]),
                                torch.stack([x[2] for x in dense]), k)
