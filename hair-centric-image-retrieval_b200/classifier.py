@@ -69,6 +69,8 @@ class KNeighborsClassifierB200:
         if self.mode == "auto" and self.use_graph:
             # fixed shape -> the whole step is one CUDA-graph launch (captured on first use)
             x, kind = _as_2d_f32(X, "X")
+            if x.shape[1] == self._bank.d and not x.is_cuda and x.shape[0] >= self.h2d_overlap_min:
+                return self._predict_host_overlapped(x, kind, T)
             sess = self._bank.session(x.shape[0], self.n_neighbors, T=T) if x.shape[1] == self._bank.d else None
             if sess is not None:
                 pred, _, _ = sess.run(x)
@@ -76,6 +78,45 @@ class KNeighborsClassifierB200:
                 return out.numpy() if isinstance(out, torch.Tensor) and not out.is_cuda else out
         out = self._bank.predict(X, self.n_neighbors, T=T, mode=self.mode)
         return out.numpy() if isinstance(out, torch.Tensor) and not out.is_cuda else out
+
+    h2d_overlap_min = 8192  # host batches at least this big: copy the bulk while a small head chunk is searched
+
+    def _predict_host_overlapped(self, x: torch.Tensor, kind: str, T):
+        """Host queries, large batch: a small HEAD chunk (1/8 of the rows, whole 128-row tiles) is
+        copied and searched first; the H2D copy of the TAIL runs on a copy stream meanwhile.  Two
+        searches cost one extra set of fixed per-search work, the hidden copy is worth ~4x that
+        (C2: 3.37 -> ~3.1 ms).  Four equal chunks were measured slower than a single shot."""
+        bank = self._bank
+        nq = x.shape[0]
+        head = max(1024, (nq // 8) // 128 * 128)
+        bounds = [(0, head), (head, nq)]
+        dev = bank.device
+        with torch.cuda.device(dev):
+            src = x if x.is_pinned() else x.contiguous().pin_memory()
+            stage = torch.empty((nq, bank.d), dtype=torch.float32, device=dev)
+            out = torch.empty((nq,), dtype=torch.int64, device=dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            cs, main = self._copy_stream, torch.cuda.current_stream()
+            cs.wait_stream(main)  # `stage` is allocated in stream order before the copies land
+            events = []
+            with torch.cuda.stream(cs):
+                for a, b in bounds:
+                    stage[a:b].copy_(src[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    events.append(ev)
+            for (a, b), ev in zip(bounds, events):
+                main.wait_event(ev)
+                sess = bank.session(b - a, self.n_neighbors, T=T)
+                if sess is not None:
+                    pred, _, _ = sess.run(stage[a:b])
+                else:
+                    pred = bank.predict(stage[a:b], self.n_neighbors, T=T, mode=self.mode)
+                out[a:b].copy_(pred)
+            stage.record_stream(cs)
+            res = _to_host(out, kind)
+        return res.numpy() if isinstance(res, torch.Tensor) and not res.is_cuda else res
 
     def predict_multi_k(self, X, ks):
         """All of ``Classifier.knn_eval``'s k values (classification_engine.py:71,79) from ONE

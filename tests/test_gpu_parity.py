@@ -529,3 +529,15 @@ def test_packed_merge_reads_gathered_blocks_in_place():
     assert torch.equal(o_i, d_i) and torch.equal(o_s, d_s) and torch.equal(o_l, d_l)
     s_ref, i_ref = GalleryBank(bank).topk(qs, k, return_device=True)
     assert torch.equal(o_i, i_ref) and torch.equal(o_s, s_ref)
+
+
+def test_overlapped_host_predict_equals_single_shot():
+    """Host batches >= 8192 rows: head chunk searched while the tail is still being copied."""
+    bank, bl = synth.make_clustered(20000, 256, 13, 71)
+    qs, _ = synth.make_clustered(9000, 256, 13, 72)
+    a = KNeighborsClassifierB200(10).fit(bank, bl.numpy()).predict(qs.numpy())
+    b = KNeighborsClassifierB200(10, use_graph=False).fit(bank, bl.numpy()).predict(qs.numpy())
+    assert a.dtype == np.int64 and a.shape == (9000,)
+    np.testing.assert_array_equal(a, b)
+    c = KNeighborsClassifierB200(10).fit(bank, bl.numpy()).predict(qs.pin_memory())
+    np.testing.assert_array_equal(c, b)
