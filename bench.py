@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph)")
     ap.add_argument("--shard", default="auto", choices=["auto", "gallery", "query"],
                     help="multi-GPU partition: gallery rows (one candidate all-gather + merge) or query replicas")
+    ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
+                    help="multi-GPU result exchange: the library's push over NVLink peer memory or one NCCL all-gather "
+                         "(default: hcir_b200.sharded.DEFAULT_EXCHANGE)")
     return ap.parse_args()
 
 
@@ -61,7 +64,7 @@ def parse():
 # clocks sampling (nvidia-smi's clocks line, via NVML) during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None
@@ -152,6 +155,27 @@ class CpuReference:
         return max(probe, min(self.qn.shape[0], want))
 
 
+def profiled_traffic(workload: str, world: int, cfg):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from
+    the committed `ncu --set full` capture of this very command (profiles/), or None when no capture
+    of this workload / partition exists."""
+    if workload != "C2" or world != 1 or cfg != dict(__import__("hcir_b200").synth.CONFIGS["C2"], tag=2):
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    try:
+        for k in json.load(open(path)):
+            if k["Kernel Name"].startswith("void simtopk_kernel<0"):
+                unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = k[key].split()
+                    tot += float(v) * unit[u]
+                return tot, "profiles/r01_ncu_full_summary.json (ncu --set full, one launch of simtopk_kernel<main>)"
+    except (OSError, KeyError, ValueError):
+        pass
+    return None, None
+
+
 def workload_cfg(args):
     from hcir_b200 import synth
     cfg = dict(synth.CONFIGS[args.workload])
@@ -236,10 +260,10 @@ def run_b200(args):
     qs, _ = synth.make_clustered(q, d, C, 4321 + tag, device=dev)  # same queries on every rank
     q_local = q if shard != "query" else ShardPlan(q, world).size(rank)
     if shard == "query":
-        gal = QueryShardedGallery(bank, bl, device=dev, classes=classes)
+        gal = QueryShardedGallery(bank, bl, device=dev, classes=classes, exchange=args.exchange)
         gb = gal.bank
     elif shard == "gallery":
-        gal = ShardedGallery(bank, bl, n_total=n, device=dev, classes=classes)
+        gal = ShardedGallery(bank, bl, n_total=n, device=dev, classes=classes, exchange=args.exchange)
         gb = gal.bank
     else:
         gb = hcir_b200.GalleryBank(bank, bl, device=dev, classes=classes)
@@ -311,6 +335,10 @@ def run_b200(args):
     value = q / (ms_per_step * 1e-3)
     sim_ms = float(np.mean(kern["simtopk"])) if "simtopk" in kern else None
     stats = dict(gb.last_stats)
+    if gal is not None:
+        stats["exchange"] = gal.exchange
+    if stats.get("uncertified"):
+        stats["completion"] = dict(gb.retry_stats)
 
     # ---- e2e through the reference-facing call with HOST buffers ----
     e2e = None
@@ -339,7 +367,10 @@ def run_b200(args):
         gbytes = n_local * d * 2.0 + q_local * d * 2.0 + q_local * k * 12.0  # bf16 bank once + queries + results
         # arithmetic intensity of the contraction = q flops per gallery byte; ridge = peak flops / peak bytes
         ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
-        common = {"kernel": "simtopk_kernel<main>", "traffic": None, "kernel_ms": sim_ms,
+        traffic, traffic_src = profiled_traffic(args.workload, world, cfg)
+        common = {"kernel": "simtopk_kernel<main>", "traffic": traffic, "traffic_unit": "bytes/launch",
+                  "traffic_source": traffic_src, "algorithmic_bytes": gbytes, "algorithmic_flops": flops,
+                  "kernel_ms": sim_ms,
                   "share_of_step": sim_ms / ms_per_step,
                   "other_kernels_ms": {kname: float(np.mean(v)) for kname, v in kern.items() if kname != "simtopk"}}
         if q_local < ridge:

@@ -51,6 +51,16 @@ SIGNATURES = {
     "hcir_merge_topk": (_INT, [_P, _P, _P, _INT, _I64, _INT, _P, _P, _P, _P]),
     "hcir_packed_block_bytes": (C.c_size_t, [_I64, _INT, _INT]),
     "hcir_merge_topk_packed": (_INT, [_P, _INT, _I64, _INT, _INT, C.c_size_t, _P, _P, _P, _P]),
+    "hcir_peer_region_bytes": (C.c_size_t, [_INT, C.c_size_t]),
+    "hcir_peer_slot_offset": (C.c_size_t, [_INT, C.c_size_t, _INT, _INT]),
+    "hcir_peer_push_ctas": (_INT, [C.c_size_t]),
+    "hcir_peer_alloc": (_INT, [C.c_size_t, C.POINTER(_P), _P]),
+    "hcir_peer_open": (_INT, [_P, C.POINTER(_P)]),
+    "hcir_peer_close": (_INT, [_P]),
+    "hcir_peer_free": (_INT, [_P]),
+    "hcir_peer_push": (_INT, [_P, C.c_size_t, C.POINTER(_P), _INT, _INT, C.c_size_t, _P, _P, _P]),
+    "hcir_peer_wait": (_INT, [_P, _INT, _P, _INT, _I64, _P]),
+    "hcir_merge_topk_peer": (_INT, [_P, _INT, _I64, _INT, _INT, C.c_size_t, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -81,7 +91,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here == ABI/header drift
         fn.restype = res
         fn.argtypes = args
-    if lib.hcir_abi_version() != 3:
+    if lib.hcir_abi_version() != 4:
         raise RuntimeError("hcir_b200: ABI version mismatch")
     _lib = lib
     return lib

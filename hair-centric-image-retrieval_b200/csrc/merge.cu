@@ -14,8 +14,15 @@ namespace hcir {
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const char* __restrict__ gsim, const char* __restrict__ gidx, const char* __restrict__ glab,
                   size_t stride_sim, size_t stride_idx, size_t stride_lab, int G, int64_t nq, int k,
-                  float* __restrict__ out_sim, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_lab) {
+                  float* __restrict__ out_sim, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_lab,
+                  const int64_t* __restrict__ step, size_t parity_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (step != nullptr) {  // peer exchange (peer.cu): this step's blocks live in parity (step & 1)
+    const size_t off = static_cast<size_t>(*step & 1) * parity_stride;
+    gsim += off;
+    gidx += off;
+    if (glab) glab += off;
+  }
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [G][k], each list descending
   const int64_t q = blockIdx.x;
   const int total = G * k;
@@ -53,7 +60,8 @@ merge_topk_kernel(const char* __restrict__ gsim, const char* __restrict__ gidx, 
 
 static int merge_launch(const void* gsim, const void* gidx, const void* glab, size_t stride_sim, size_t stride_idx,
                         size_t stride_lab, int G, int64_t nq, int k, float* out_sim, int64_t* out_idx,
-                        int32_t* out_lab, hcir_stream_t stream) {
+                        int32_t* out_lab, hcir_stream_t stream, const int64_t* step = nullptr,
+                        size_t parity_stride = 0) {
   HCIR_REQUIRE(G > 0 && nq >= 0 && k > 0, "merge_topk: bad shape G=%d nq=%lld k=%d", G, (long long)nq, k);
   HCIR_REQUIRE((gsim && gidx && out_sim && out_idx) || nq == 0, "merge_topk: null pointer");
   HCIR_REQUIRE((out_lab == nullptr) || (glab != nullptr), "merge_topk: out_lab without gathered labels");
@@ -66,7 +74,7 @@ static int merge_launch(const void* gsim, const void* gidx, const void* glab, si
                                      static_cast<int>(smem)));
   merge_topk_kernel<<<static_cast<unsigned>(nq), 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const char*>(gsim), static_cast<const char*>(gidx), static_cast<const char*>(glab), stride_sim,
-      stride_idx, stride_lab, G, nq, k, out_sim, out_idx, out_lab);
+      stride_idx, stride_lab, G, nq, k, out_sim, out_idx, out_lab, step, parity_stride);
   HCIR_CUDA_TRY(cudaGetLastError());
   return HCIR_OK;
 }
@@ -87,9 +95,9 @@ extern "C" size_t hcir_packed_block_bytes(int64_t nq, int k, int with_labels) {
   return (b + 15) / 16 * 16;  // every rank's block starts 16-byte aligned in the gathered buffer
 }
 
-extern "C" int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int with_labels,
-                                      size_t rank_stride_bytes, float* out_sim, int64_t* out_idx, int32_t* out_lab,
-                                      hcir_stream_t stream) {
+static int merge_packed(const void* gathered, int G, int64_t nq, int k, int with_labels, size_t rank_stride_bytes,
+                        float* out_sim, int64_t* out_idx, int32_t* out_lab, hcir_stream_t stream,
+                        const int64_t* step, size_t parity_stride) {
   using namespace hcir;
   HCIR_REQUIRE(gathered != nullptr || nq == 0, "merge_topk_packed: null pointer");
   const size_t e = static_cast<size_t>(nq > 0 ? nq : 0) * static_cast<size_t>(k > 0 ? k : 0);
@@ -100,5 +108,23 @@ extern "C" int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, i
   const char* base = static_cast<const char*>(gathered);
   // block layout: idx (8-byte aligned first) | sims | labels
   return merge_launch(base + e * 8, base, with_labels ? base + e * 12 : nullptr, block, block, block, G, nq, k,
-                      out_sim, out_idx, with_labels ? out_lab : nullptr, stream);
+                      out_sim, out_idx, with_labels ? out_lab : nullptr, stream, step, parity_stride);
+}
+
+extern "C" int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int with_labels,
+                                      size_t rank_stride_bytes, float* out_sim, int64_t* out_idx, int32_t* out_lab,
+                                      hcir_stream_t stream) {
+  return merge_packed(gathered, G, nq, k, with_labels, rank_stride_bytes, out_sim, out_idx, out_lab, stream, nullptr,
+                      0);
+}
+
+extern "C" int hcir_merge_topk_peer(const void* region_local, int G, int64_t nq, int k, int with_labels,
+                                    size_t slot_bytes, const int64_t* step, float* out_sim, int64_t* out_idx,
+                                    int32_t* out_lab, hcir_stream_t stream) {
+  using namespace hcir;
+  HCIR_REQUIRE(region_local != nullptr && step != nullptr, "merge_topk_peer: null pointer");
+  const size_t stride = (slot_bytes + 255) / 256 * 256;
+  const char* data = static_cast<const char*>(region_local) + hcir_peer_slot_offset(G, slot_bytes, 0, 0);
+  return merge_packed(data, G, nq, k, with_labels, stride, out_sim, out_idx, out_lab, stream, step,
+                      static_cast<size_t>(G) * stride);
 }

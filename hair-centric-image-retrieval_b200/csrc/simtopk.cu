@@ -468,6 +468,64 @@ __device__ __forceinline__ uint32_t kth_u32(const uint32_t* vals, int n, int k, 
   return prefix;
 }
 
+// Two order statistics of vals[0..n) at once (kA-th and kB-th largest, ordered bits in shared
+// memory) by an MSB-first radix select, 8 bits per pass, the whole CTA cooperating: 4 passes of
+// {clear 2 x 256 bins, histogram the values that still match each prefix, one warp per statistic
+// walks its bins from the top}.  12 barriers in all (the bitwise search needed ~250).
+__device__ __forceinline__ void kth2_block(const uint32_t* vals, int n, int kA, int kB, uint32_t* hist,
+                                           uint32_t* sh, uint32_t& outA, uint32_t& outB) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t prefA = 0u, prefB = 0u;
+  int remA = kA, remB = kB;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 512; i += kThrBlockThreads) hist[i] = 0u;
+    __syncthreads();
+    const uint32_t hmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < n; i += kThrBlockThreads) {
+      const uint32_t v = vals[i], bin = (v >> shift) & 255u;
+      if ((v & hmask) == prefA) atomicAdd(&hist[bin], 1u);
+      if ((v & hmask) == prefB) atomicAdd(&hist[256 + bin], 1u);
+    }
+    __syncthreads();
+    if (warp < 2) {
+      const uint32_t* h = hist + warp * 256;
+      const int rem = warp == 0 ? remA : remB;
+      uint32_t b[8];
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        b[j] = h[255 - (lane * 8 + j)];
+        c += static_cast<int>(b[j]);
+      }
+      int incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += t;
+      }
+      const int excl = incl - c;
+      if (excl < rem && incl >= rem) {  // exactly one lane: rem <= number of matching values
+        int r = rem - excl, bin = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (r > 0 && r <= static_cast<int>(b[j])) { bin = 255 - (lane * 8 + j); sh[warp * 2 + 1] = r; r = 0; }
+          else if (r > 0) r -= static_cast<int>(b[j]);
+        }
+        sh[warp * 2] = static_cast<uint32_t>(bin);
+      }
+    }
+    __syncthreads();
+    prefA |= sh[0] << shift;
+    remA = static_cast<int>(sh[1]);
+    prefB |= sh[2] << shift;
+    remB = static_cast<int>(sh[3]);
+  }
+  outA = prefA;
+  outB = prefB;
+}
+
 template <bool kBlock>
 __global__ void __launch_bounds__(kBlock ? kThrBlockThreads : kThrWarps * kWarp)
 threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int kc, int hint_rank,
@@ -476,16 +534,24 @@ threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = kBlock ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kThrWarps + warp;
   if (q >= nq) return;  // warp-uniform (block-uniform for kBlock)
-  uint32_t* red = reinterpret_cast<uint32_t*>(smem_raw);  // [4] block-reduction scratch
-  uint32_t* vals = red + 4 + (kBlock ? 0 : static_cast<size_t>(warp) * num_chunks);
+  uint32_t* red = reinterpret_cast<uint32_t*>(smem_raw);  // [4] scratch
+  uint32_t* hist = red + 4;                               // [2][256] (kBlock only)
+  uint32_t* vals = red + 4 + (kBlock ? 512 : static_cast<size_t>(warp) * num_chunks);
   const float* src = cmax + q * static_cast<int64_t>(num_chunks);
   const int tid = kBlock ? threadIdx.x : lane, nthr = kBlock ? kThrBlockThreads : kWarp;
   for (int i = tid; i < num_chunks; i += nthr) vals[i] = f2ord(src[i]);
   if (kBlock) __syncthreads(); else __syncwarp();
   float t = -INFINITY, h = -INFINITY;
   if (num_chunks >= kc) {
-    t = ord2f(kth_u32<kBlock>(vals, num_chunks, kc, red));
-    h = ord2f(kth_u32<kBlock>(vals, num_chunks, hint_rank, red));
+    if constexpr (kBlock) {
+      uint32_t a, b;
+      kth2_block(vals, num_chunks, kc, hint_rank, hist, red, a, b);
+      t = ord2f(a);
+      h = ord2f(b);
+    } else {
+      t = ord2f(kth_u32<false>(vals, num_chunks, kc, red));
+      h = ord2f(kth_u32<false>(vals, num_chunks, hint_rank, red));
+    }
   }
   if (tid == 0) {
     thr0[q] = t;
@@ -645,7 +711,7 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     HCIR_REQUIRE(plan->hint_rank >= 1 && plan->hint_rank <= plan->kc, "simtopk: bad hint_rank=%d", plan->hint_rank);
     float* thr_hi = reinterpret_cast<float*>(ws + plan->thr_hi_off);
     const bool per_block = nq <= 1024;  // few queries: a CTA per query hides the search latency
-    const size_t smem = 16 + static_cast<size_t>(per_block ? 1 : kThrWarps) * plan->num_chunks * 4;
+    const size_t smem = 16 + (per_block ? 2048 : 0) + static_cast<size_t>(per_block ? 1 : kThrWarps) * plan->num_chunks * 4;
     HCIR_REQUIRE(smem <= 200 * 1024, "simtopk: %d sample chunks do not fit in shared memory", plan->num_chunks);
     if (per_block) {
       HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -150,6 +150,7 @@ class GalleryBank:
         if labels is not None:
             self.set_labels(labels, classes)
         self.last_stats = {}
+        self.retry_stats = {}   # how the last batch of uncertified queries was completed
         # bench.py sets this to a list to get (name, start_event, end_event) per kernel launch
         self.kernel_events = None
         self.launches = 0  # number of hcir kernels launched by this bank since construction
@@ -263,12 +264,70 @@ class GalleryBank:
         res = tail(out_sim, out_idx) if tail else None
         n_unc = int(unc_cnt.item())  # 4-byte readback: decides whether the exact fallback runs
         if n_unc > 0:
-            self._exact(q32, unc_list, n_unc, k, out_sim, out_idx)
+            self._finish_uncertified(q32, qbf, qdl, unc_list, n_unc, k, out_sim, out_idx)
             res = tail(out_sim, out_idx) if tail else None
         self.last_stats = {"path": "tensor", "uncertified": n_unc, "nsplit": int(plan.nsplit),
                            "kc": int(plan.kc), "cap": int(plan.cap), "workspace_bytes": int(plan.bytes),
                            "sample_rows": int(plan.sample_rows), "chunk_w": int(plan.chunk_w)}
         return out_sim, out_idx, res
+
+    def _finish_uncertified(self, q32, qbf, qdl, unc_list, n_unc, k, out_sim, out_idx):
+        """Complete the queries K3 could not certify (their kc best bf16 candidates do not provably
+        contain the fp32 top-k).  First a SECOND tensor pass over just these queries with an explicit
+        threshold: K3 left each one's best-so-far fp32 k-th score s_k, a true top-k row scores
+        >= s_k in fp32, hence > s_k - eps in bf16, so the main pass with thr = s_k - eps (no sample
+        pass) and a 4x wider kc collects every row that can matter, and K3 certifies against that
+        very threshold.  Costs one gallery stream (the streaming regime) instead of an fp32 brute
+        force.  What even that cannot certify (more than 4*kc rows inside the eps band: duplicated
+        galleries) goes to the exact CUDA-core kernel."""
+        lib, dev = self.lib, self.device
+        kc = self.choose_kc(k)
+        plan = Plan()
+        for mult in (4, 3, 2, 1):   # widest kc whose plan still carries per-query thresholds
+            kc2 = max(kc, min(mult * kc, 2048))
+            _lib.check(lib.hcir_simtopk_plan(n_unc, self.n, self.ld, kc2, self.sm_count, plan), "simtopk_plan")
+            if plan.sample_rows > 0:
+                break
+        if plan.sample_rows <= 0 or qbf is None:
+            self._exact(q32, unc_list, n_unc, k, out_sim, out_idx)
+            self.retry_stats = {"second_pass": 0, "exact": int(n_unc)}
+            return
+        sel = unc_list[:n_unc].long()
+        dq = qdl[sel]
+        eps = self.g_delta_max * (1.0 + dq) + dq * (1.0 + 1e-6) + self.eps_acc
+        thr = (out_sim[sel, k - 1] - eps * 1.001 - 1e-6).float().contiguous()
+        rows = -(-n_unc // 128) * 128
+        qbf2 = torch.zeros((rows, self.ld), dtype=torch.bfloat16, device=dev)
+        qbf2[:n_unc] = qbf[sel]
+        q32_2 = q32[sel].contiguous()
+        dq = dq.contiguous()
+        plan.q_rows = rows
+        ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
+        for off in (int(plan.thr0_off), int(plan.thr_hi_off)):   # the thresholds the sample pass would write
+            ws[off: off + 4 * n_unc].view(torch.float32).copy_(thr)
+        st = _stream_ptr()
+        plan.flags = 4  # HCIR_FLAG_MAIN_ONLY: thresholds are given
+        _lib.check(self._timed("simtopk_retry", lambda: lib.hcir_simtopk(
+            qbf2.data_ptr(), n_unc, self.gbf.data_ptr(), self.n, self.ld, plan, ws.data_ptr(), st)), "simtopk(retry)")
+        plan.flags = 0
+        o_s = torch.empty((n_unc, k), dtype=torch.float32, device=dev)
+        o_i = torch.empty((n_unc, k), dtype=torch.int64, device=dev)
+        unc2 = torch.empty((n_unc,), dtype=torch.int32, device=dev)
+        cnt2 = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(self._timed("select_rescore_retry", lambda: lib.hcir_select_rescore(
+            q32_2.data_ptr(), self.g32.data_ptr(), self.ld, n_unc, self.n, k, self.idx_offset, plan, ws.data_ptr(),
+            dq.data_ptr(), self.g_delta_max, self.eps_acc, o_s.data_ptr(), o_i.data_ptr(), unc2.data_ptr(),
+            cnt2.data_ptr(), st)), "select_rescore(retry)")
+        n2 = int(cnt2.item())
+        if n2 < n_unc:
+            ok = torch.ones((n_unc,), dtype=torch.bool, device=dev)
+            ok[unc2[:n2].long()] = False
+            out_sim[sel[ok]] = o_s[ok]
+            out_idx[sel[ok]] = o_i[ok]
+        if n2 > 0:
+            left = unc_list[:n_unc][unc2[:n2].long()].contiguous()
+            self._exact(q32, left, n2, k, out_sim, out_idx)
+        self.retry_stats = {"second_pass": int(n_unc - n2), "exact": int(n2)}
 
     def _exact(self, q32, qlist, nlist, k, out_sim, out_idx):
         lib = self.lib
@@ -503,7 +562,7 @@ class SearchSession:
     def finish_uncertified(self, n_unc: int):
         """Eager completion of the (rare) queries the tensor path could not certify."""
         b = self.bank
-        b._exact(self.q32, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
+        b._finish_uncertified(self.q32, self.qbf, self.qdl, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
         if self.out_lab is not None:
             self._gather_packed_labels()
 
@@ -524,7 +583,8 @@ class SearchSession:
             n_unc = int(self.unc_cnt.item())
             pred = self.pred
             if n_unc > 0:
-                b._exact(self.q32, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
+                b._finish_uncertified(self.q32, self.qbf, self.qdl, self.unc_list, n_unc, self.k, self.out_sim,
+                                      self.out_idx)
                 if self.vote:
                     pred = self._tail()
                 if self.out_lab is not None:

@@ -1,0 +1,145 @@
+"""Exchange of per-rank result blocks over NVLink peer memory (csrc/peer.cu): the path's own
+all-gather.  Every rank stores its block straight into a slot of EVERY rank's region with plain
+16-byte stores (the regions are cudaMalloc'd by the library, exported with CUDA IPC and mapped by
+all ranks of the box), bumps an arrival counter behind a system-scope fence, and a one-warp kernel
+on each rank spins until all blocks of the step have landed.  No collective-library call sits on
+the data path, and because the step counter lives in device memory the push / wait pair is
+captured into the search step's CUDA graph and replayed unchanged.
+
+``torch.distributed`` is used once, at construction, to trade the 64-byte IPC handles (SURVEY.md
+section 8e "later fusion"; no reference analogue -- the reference's kNN is single-process CPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+_HDR_WORDS = 64          # 512-byte header, int64 words (peer.cu)
+_HDR_META, _HDR_STEP, _HDR_ERR, _PEER_MAX = 16, 48, 49, 16
+
+
+class _DeviceBytes:
+    """A raw device allocation presented through the CUDA array interface (torch.as_tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerExchange:
+    """One exchange channel: ``slot_bytes`` per rank and step.  Construction is COLLECTIVE over
+    ``group`` (IPC handle all-gather + barrier) and must happen outside CUDA-graph capture."""
+
+    def __init__(self, slot_bytes: int, *, group=None, device=None, timeout_s: float = 5.0):
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _PEER_MAX:
+            raise ValueError(f"peer exchange supports up to {_PEER_MAX} ranks, got {self.world}")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.slot_bytes = int(-(-int(slot_bytes) // 16) * 16)
+        self.stride = -(-self.slot_bytes // 256) * 256
+        self.timeout_ns = int(timeout_s * 1e9)
+        total = int(self.lib.hcir_peer_region_bytes(self.world, self.slot_bytes))
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hcir_peer_alloc(total, C.byref(ptr), handle), "peer_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self._local_ptr = int(ptr.value)
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(self._local_ptr)
+                    continue
+                p = C.c_void_p()
+                _lib.check(self.lib.hcir_peer_open(C.create_string_buffer(handles[r], 64), C.byref(p)),
+                           f"peer_open(rank {r})")
+                ptrs.append(int(p.value))
+            self._ptrs = ptrs
+            self._regions = (C.c_void_p * self.world)(*ptrs)
+            self._mem = _DeviceBytes(self._local_ptr, total)
+            self.local = torch.as_tensor(self._mem, device=self.device)        # uint8 view of the local region
+            self.step = torch.zeros((), dtype=torch.int64, device=self.device)  # device-side step counter
+            self._hdr_host = torch.empty((_HDR_WORDS,), dtype=torch.int64, pin_memory=True)
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group)   # every region is zeroed and mapped everywhere before the first push
+        self.host_step = 0
+        self.ctas = 1
+        self.block_bytes = None
+        self._closed = False
+
+    # ------------------------------------------------------------------ data path (capturable)
+    def exchange(self, block: torch.Tensor, meta: torch.Tensor | None = None):
+        """Enqueue: step += 1, push ``block`` (contiguous bytes, multiple of 16) + the int32 ``meta``
+        word into every rank's region, wait for every rank's block of this step."""
+        nbytes = block.numel() * block.element_size()
+        if not block.is_contiguous() or nbytes % 16 or nbytes > self.slot_bytes:
+            raise ValueError(f"peer exchange block must be contiguous, a multiple of 16 bytes and <= {self.slot_bytes}")
+        if self.block_bytes not in (None, nbytes):   # arrivals are counted per step: one block size per channel
+            raise ValueError(f"peer exchange channel carries blocks of {self.block_bytes} bytes, got {nbytes}")
+        self.block_bytes = nbytes
+        st = torch.cuda.current_stream().cuda_stream
+        self.step.add_(1)
+        self.ctas = int(self.lib.hcir_peer_push_ctas(nbytes))
+        _lib.check(self.lib.hcir_peer_push(block.data_ptr(), nbytes, self._regions, self.world, self.rank,
+                                           self.slot_bytes, self.step.data_ptr(),
+                                           meta.data_ptr() if meta is not None else None, st), "peer_push")
+        _lib.check(self.lib.hcir_peer_wait(self._local_ptr, self.world, self.step.data_ptr(), self.ctas,
+                                           self.timeout_ns, st), "peer_wait")
+        if not torch.cuda.is_current_stream_capturing():
+            self.host_step += 1
+
+    def note_replay(self):
+        """A CUDA graph holding one captured ``exchange`` was replayed."""
+        self.host_step += 1
+
+    # ------------------------------------------------------------------ reading the result
+    @property
+    def local_ptr(self) -> int:
+        return self._local_ptr
+
+    def header(self) -> np.ndarray:
+        """Synchronising read of the local header; raises if a wait timed out or the device step
+        differs from the host's count (a rank skipped or repeated a step)."""
+        self._hdr_host.copy_(self.local[: _HDR_WORDS * 8].view(torch.int64), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self._hdr_host.numpy()
+        if h[_HDR_ERR] != 0:
+            raise RuntimeError(f"peer exchange: rank {self.rank} timed out waiting for a peer's block at step "
+                               f"{int(h[_HDR_ERR])}")
+        if int(h[_HDR_STEP]) != self.host_step:
+            raise RuntimeError(f"peer exchange: device step {int(h[_HDR_STEP])} != host step {self.host_step}")
+        return h
+
+    def metas(self, header: np.ndarray | None = None) -> list[int]:
+        h = self.header() if header is None else header
+        par = self.host_step & 1
+        return [int(v) for v in h[_HDR_META + par * _PEER_MAX: _HDR_META + par * _PEER_MAX + self.world]]
+
+    def gathered(self) -> torch.Tensor:
+        """[world, stride] uint8 view of the blocks of the LAST completed step (valid until the
+        step after next)."""
+        off = int(self.lib.hcir_peer_slot_offset(self.world, self.slot_bytes, self.host_step & 1, 0))
+        return self.local[off: off + self.world * self.stride].view(self.world, self.stride)
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for r, p in enumerate(self._ptrs):
+                if r != self.rank:
+                    self.lib.hcir_peer_close(p)
+            try:
+                dist.barrier(self.group)   # nobody frees a region a peer still maps
+            except Exception:
+                pass
+            self.local = None
+            self.lib.hcir_peer_free(self._local_ptr)

@@ -14,8 +14,15 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+import os
+
 from . import _lib
 from .engine import GalleryBank, _as_2d_f32, _stream_ptr, _to_host
+from .peer import PeerExchange
+
+# how the per-rank result blocks travel: "peer" = the library's own push over NVLink peer memory
+# (csrc/peer.cu, captured into the step's CUDA graph), "nccl" = one ncclAllGather
+DEFAULT_EXCHANGE = os.environ.get("HCIR_EXCHANGE", "nccl")
 
 
 @dataclass(frozen=True)
@@ -90,7 +97,10 @@ class ShardedGallery:
     sort-merge on (sim desc, idx asc))."""
 
     def __init__(self, features_local, labels_local=None, *, n_total: int, group=None, device=None,
-                 classes=None):
+                 classes=None, exchange: str | None = None):
+        self.exchange = exchange or DEFAULT_EXCHANGE
+        if self.exchange not in ("peer", "nccl"):
+            raise ValueError(f"unknown exchange {self.exchange!r}")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -122,6 +132,33 @@ class ShardedGallery:
         return sims, idx
 
     def _post(self, sess, want_vote: bool, T):
+        return self._post_peer(sess, want_vote, T) if self.exchange == "peer" else self._post_nccl(sess, want_vote, T)
+
+    def _post_peer(self, sess, want_vote: bool, T):
+        """Tail of the step, captured into the same CUDA graph as the local search: this rank's packed
+        block is PUSHED into every rank's peer region over NVLink (its uncertified count rides along
+        as the meta word), a one-warp kernel waits for all blocks of the step, K5 reads them in
+        place, then (predict) the vote.  No collective-library call on the data path."""
+        lib, dev = self.bank.lib, self.device
+        nq, k = sess.nq, sess.k
+        has_lab = sess.out_lab is not None
+        xc = getattr(sess, "xchg", None)
+        if xc is None:   # first (eager warm-up) pass of the session body: collective allocation
+            xc = sess.xchg = PeerExchange(sess.block_bytes, group=self.group, device=dev)
+        xc.exchange(sess.pack[: sess.block_bytes], meta=sess.unc_cnt)
+        o_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        o_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        o_l = torch.empty((nq, k), dtype=torch.int32, device=dev) if has_lab else None
+        self.bank.launches += 3
+        _lib.check(lib.hcir_merge_topk_peer(xc.local_ptr, self.world, nq, k, int(has_lab), xc.slot_bytes,
+                                            xc.step.data_ptr(), o_s.data_ptr(), o_i.data_ptr(),
+                                            o_l.data_ptr() if has_lab else None, _stream_ptr()), "merge_topk_peer")
+        pred = None
+        if want_vote:
+            pred = self.bank._classes_device()[self.bank.vote(o_s, o_l, T=T).long()]
+        return {"gathered": None, "xchg": xc, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
+
+    def _post_nccl(self, sess, want_vote: bool, T):
         """Tail of the step, captured into the same CUDA graph as the local search: ONE all-gather
         of every rank's packed block (+ trailer = its uncertified count), K5 reading the gathered
         blocks in place, and (predict) the vote."""
@@ -145,7 +182,7 @@ class ShardedGallery:
 
     def _step_packed(self, q: torch.Tensor, k: int, want_vote: bool, T):
         """Whole multi-GPU step as ONE graph launch per rank; None if the tensor path does not apply."""
-        key = ("gallery-sharded", want_vote, None if T is None else float(T))
+        key = ("gallery-sharded", self.exchange, want_vote, None if T is None else float(T))
         sess = self.bank.session(q.shape[0], k, vote=False, profile=self.profile, pack=True,
                                  post=lambda s_: self._post(s_, want_vote, T), post_key=key)
         if sess is None or (want_vote and sess.out_lab is None):
@@ -153,15 +190,19 @@ class ShardedGallery:
         sess.run(q, check=False)
         self.last_session = sess
         out = sess.post_out
-        # every rank sees every rank's uncertified count in the gathered trailers: the (rare) exact
+        # every rank sees every rank's uncertified count (gathered trailers / meta words): the (rare)
         # completion and the repeated exchange are taken by ALL ranks or by none
-        stride = sess.pack.numel()
-        counts = out["gathered"].view(self.world, stride)[:, sess.block_bytes: sess.block_bytes + 4].contiguous()
-        counts = counts.view(torch.int32).view(-1).tolist()
+        if out.get("xchg") is not None:
+            out["xchg"].note_replay()
+            counts = out["xchg"].metas()
+        else:
+            stride = sess.pack.numel()
+            counts = out["gathered"].view(self.world, stride)[:, sess.block_bytes: sess.block_bytes + 4].contiguous()
+            counts = counts.view(torch.int32).view(-1).tolist()
         if any(c > 0 for c in counts):
             if counts[self.rank] > 0:
                 sess.finish_uncertified(counts[self.rank])
-            out = self._post(sess, want_vote, T)
+            out = self._post_nccl(sess, want_vote, T)
         self.bank.last_stats = {"path": "tensor+graph", "uncertified": int(sum(counts)),
                                 "nsplit": int(sess.plan.nsplit), "kc": int(sess.plan.kc), "cap": int(sess.plan.cap),
                                 "workspace_bytes": int(sess.plan.bytes), "sample_rows": int(sess.plan.sample_rows),
@@ -245,7 +286,10 @@ class QueryShardedGallery:
     every rank.  Results are bit-identical to the single-GPU result by construction (each query is
     answered by exactly the single-GPU code path)."""
 
-    def __init__(self, features, labels=None, *, group=None, device=None, classes=None):
+    def __init__(self, features, labels=None, *, group=None, device=None, classes=None, exchange: str | None = None):
+        self.exchange = exchange or DEFAULT_EXCHANGE
+        if self.exchange not in ("peer", "nccl"):
+            raise ValueError(f"unknown exchange {self.exchange!r}")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -261,12 +305,60 @@ class QueryShardedGallery:
     def _gather_rows(self, local: torch.Tensor, sp: ShardPlan) -> torch.Tensor:
         return gather_rows(local, sp, self.group)
 
+    def _post_peer(self, sess, hmax: int):
+        """Captured at the end of the local step's graph: this rank's predictions are pushed into
+        every rank's peer region over NVLink (uncertified count as the meta word) and a one-warp
+        kernel waits for everybody's block."""
+        nwords = -(-hmax // 2) * 2   # 16-byte multiple
+        xc = getattr(sess, "xchg", None)
+        if xc is None:   # eager warm-up pass of the session body: collective allocation
+            xc = sess.xchg = PeerExchange(nwords * 8, group=self.group, device=self.device)
+        blk = torch.zeros((nwords,), dtype=torch.int64, device=self.device)
+        blk[: sess.nq].copy_(sess.pred)
+        self.bank.launches += 2
+        xc.exchange(blk.view(torch.uint8), meta=sess.unc_cnt)
+        return {"xchg": xc}
+
+    def _predict_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
+        """Whole step = one graph launch per rank incl. the result exchange; None if not applicable."""
+        sizes = [sp.size(r) for r in range(self.world)]
+        if min(sizes) < 1 or not self.bank.use_tensor_path(mine.shape[0], k):   # same decision on every rank
+            return None
+        hmax = max(sizes)
+        sess = self.bank.session(mine.shape[0], k, T=T, profile=self.profile,
+                                 post=lambda s_: self._post_peer(s_, hmax), post_key=("query-sharded", hmax))
+        if sess is None:
+            return None
+        sess.run(mine, check=False)
+        self.last_session = sess
+        xc = sess.post_out["xchg"]
+        xc.note_replay()
+        counts = xc.metas()
+        self.bank.last_stats = {"path": "tensor+graph", "uncertified": int(sum(counts)),
+                                "nsplit": int(sess.plan.nsplit), "kc": int(sess.plan.kc), "cap": int(sess.plan.cap),
+                                "workspace_bytes": int(sess.plan.bytes), "sample_rows": int(sess.plan.sample_rows),
+                                "chunk_w": int(sess.plan.chunk_w), "exchange": "peer"}
+        if any(c > 0 for c in counts):   # rare: every rank takes the completion + collective gather
+            pred = sess.pred
+            if counts[self.rank] > 0:
+                sess.finish_uncertified(counts[self.rank])
+                pred = sess._tail()
+            return self._gather_rows(pred, sp)
+        g = xc.gathered()[:, : hmax * 8]
+        if all(sz == hmax for sz in sizes) and xc.stride == hmax * 8:
+            return g.reshape(-1).view(torch.int64).clone()   # the region is reused two steps later
+        return torch.cat([g[r, : sizes[r] * 8].contiguous().view(torch.int64) for r in range(self.world)], 0)
+
     def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
         q, kind = _as_2d_f32(queries, "queries")
         sp, mine = self._slice(q)
         with torch.cuda.device(self.device):
             if not mine.is_cuda:
                 mine = mine.contiguous().to(self.device, non_blocking=True)
+            if self.exchange == "peer" and mode == "auto":
+                out = self._predict_peer(mine, sp, int(k), T)
+                if out is not None:
+                    return _to_host(out, kind)
             sess = self.bank.session(mine.shape[0], int(k), T=T, profile=self.profile) if mode == "auto" else None
             if sess is not None:
                 pred, _, _ = sess.run(mine)   # the whole local step is one CUDA-graph launch

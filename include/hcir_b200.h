@@ -35,7 +35,7 @@ extern "C" {
 #define HCIR_ECUDA (-3)      /* a CUDA runtime / driver call failed                        */
 #define HCIR_EWORKSPACE (-4) /* workspace too small                                        */
 
-#define HCIR_ABI_VERSION 3
+#define HCIR_ABI_VERSION 4
 
 /* hcir_plan_t.flags: measurement aids, all 0 in production */
 #define HCIR_FLAG_NO_EMIT 1     /* main pass emits nothing: pure contraction throughput        */
@@ -180,6 +180,36 @@ size_t hcir_packed_block_bytes(int64_t nq, int k, int with_labels);
 int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int with_labels,
                            size_t rank_stride_bytes, float* out_sim, int64_t* out_idx, int32_t* out_lab,
                            hcir_stream_t stream);
+
+/* ---- candidate / result exchange over NVLink peer memory (new design, no reference analogue;
+ * SURVEY.md section 8e "later fusion") ------------------------------------------------------
+ * One REGION of device memory per rank, exported with CUDA IPC and mapped by every other rank of
+ * the box; layout: 512-byte header (arrival counters, one int64 "meta" word per rank and parity,
+ * last completed step, error word) + 2 parities x world slots of round_up(slot_bytes, 256).
+ *   hcir_peer_alloc   cudaMalloc + zero + IPC export (64-byte handle) of this rank's region
+ *   hcir_peer_open    map a peer's region from its handle;  hcir_peer_close / hcir_peer_free undo
+ *   hcir_peer_push    store `bytes` (multiple of 16) of this rank's block into slot (step&1, rank) of
+ *                     EVERY region in regions[0..world) (host array; own region included), plus the
+ *                     int32 at meta_src (nullable) as this rank's meta word, then signal arrival.
+ *                     `step` is a device int64 the caller increments on the stream before the push.
+ *   hcir_peer_wait    spin (bounded by timeout_ns; on expiry header word 49 is set to the step)
+ *                     until every rank's block of this step has landed in the LOCAL region
+ *   hcir_merge_topk_peer   K5 reading this step's gathered blocks in place from the local region */
+size_t hcir_peer_region_bytes(int world, size_t slot_bytes);
+size_t hcir_peer_slot_offset(int world, size_t slot_bytes, int parity, int rank);
+int hcir_peer_push_ctas(size_t bytes);
+int hcir_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_64);
+int hcir_peer_open(const void* ipc_handle_64, void** ptr);
+int hcir_peer_close(void* ptr);
+int hcir_peer_free(void* ptr);
+int hcir_peer_push(const void* src, size_t bytes, void* const* regions, int world, int rank,
+                   size_t slot_bytes, const int64_t* step, const int32_t* meta_src,
+                   hcir_stream_t stream);
+int hcir_peer_wait(void* region_local, int world, const int64_t* step, int ctas_per_push,
+                   int64_t timeout_ns, hcir_stream_t stream);
+int hcir_merge_topk_peer(const void* region_local, int G, int64_t nq, int k, int with_labels,
+                         size_t slot_bytes, const int64_t* step, float* out_sim, int64_t* out_idx,
+                         int32_t* out_lab, hcir_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,79 @@
+"""Multi-GPU parity worker (one rank per GPU; launched by tests/test_multigpu.py or by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29611 tests/mgpu_worker.py
+Every sharded answer must be BIT-identical to the single-GPU answer of the same inputs, for both
+partitions (gallery rows / query replicas) and both exchanges (the library's push over NVLink peer
+memory / one NCCL all-gather), including the steps that take the uncertified-completion branch."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import hcir_b200  # noqa: E402
+from hcir_b200 import synth  # noqa: E402
+from hcir_b200.sharded import QueryShardedGallery, ShardPlan, ShardedGallery  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    checks = 0
+
+    def case(bank, bl, qs, k, tag, expect_uncertified=False):
+        nonlocal checks
+        n = bank.shape[0]
+        ref = hcir_b200.GalleryBank(bank, bl, device=dev)
+        p_ref, s_ref, i_ref = ref.predict(qs, k, return_neighbors=True)
+        if expect_uncertified:
+            assert ref.last_stats["uncertified"] > 0, tag
+        sp = ShardPlan(n, world)
+        lo, hi = sp.start(rank), sp.stop(rank)
+        for exchange in ("peer", "nccl"):
+            gal = ShardedGallery(bank[lo:hi], bl[lo:hi], n_total=n, device=dev, classes=ref.classes_,
+                                 exchange=exchange)
+            for rep in range(3):   # replays alternate the two parities of the peer region
+                s, i = gal.topk(qs, k)
+                assert torch.equal(i, i_ref) and torch.equal(s, s_ref), (tag, exchange, "gallery topk", rep)
+                p = gal.predict(qs, k)
+                assert torch.equal(p, p_ref), (tag, exchange, "gallery predict", rep)
+            if expect_uncertified:
+                assert gal.bank.last_stats["uncertified"] > 0, (tag, exchange)
+            qg = QueryShardedGallery(bank, bl, device=dev, classes=ref.classes_, exchange=exchange)
+            for rep in range(3):
+                p = qg.predict(qs, k)
+                assert torch.equal(p, p_ref), (tag, exchange, "query predict", rep)
+                p = qg.predict(qs.cuda(), k)
+                assert torch.equal(p.cpu(), p_ref), (tag, exchange, "query predict (device queries)", rep)
+            checks += 1
+            del gal, qg
+        del ref
+        torch.cuda.empty_cache()
+
+    bank, bl = synth.make_clustered(40000, 256, 13, 91)
+    qs, _ = synth.make_clustered(1001, 256, 13, 92)          # ragged: 1001 queries over `world` ranks
+    case(bank, bl, qs, 20, "clustered")
+    case(bank[:30011], bl[:30011], qs[:257], 7, "ragged gallery")
+    # near-duplicate gallery: every query is uncertified -> the collective completion branch
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1, 256, generator=g)
+    dup = base + 1e-4 * torch.randn(16384, 256, generator=g)
+    qd = base + 1e-4 * torch.randn(256, 256, generator=g)
+    case(dup, torch.arange(16384) % 5, qd, 10, "near-duplicates", expect_uncertified=True)
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK world={world} cases={checks}")
+    sys.stdout.flush()
+    os._exit(0)   # captured collectives keep the communicator busy at teardown (see bench.py)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_builds_and_loads():
     lib = _lib.load()
     assert os.path.exists(_build.LIB_PATH)
-    assert lib.hcir_abi_version() == 3
+    assert lib.hcir_abi_version() == 4
     assert lib.hcir_padded_dim(768) == 768 and lib.hcir_padded_dim(512) == 512
     assert lib.hcir_padded_dim(100) == 128 and lib.hcir_padded_dim(2048) == 2048
 

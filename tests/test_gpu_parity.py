@@ -417,6 +417,26 @@ def test_kth_neighbour_matches_neg_sampler_static():
         assert same.float().mean() > 0.99
     assert torch.equal(metrics.kth_neighbour(emb, 1), torch.arange(256))  # rank 1 is the row itself
 
+def test_uncertified_queries_are_finished_by_a_second_tensor_pass():
+    """300 near-identical neighbours per query: the kc = 84 best bf16 candidates cannot certify the
+    fp32 top-10, but the second pass (threshold = best-so-far k-th score - eps, kc x 4) collects the
+    whole band and certifies it -- no fp32 brute force, results identical to the exact path."""
+    d = 256
+    g = torch.Generator().manual_seed(11)
+    bases = torch.randn(8, d, generator=g)
+    dense = (bases[:, None, :] + 1e-3 * torch.randn(8, 300, d, generator=g)).reshape(-1, d)
+    bank = torch.cat([torch.randn(20000, d, generator=g), dense])[torch.randperm(22400, generator=g)]
+    qs = bases.repeat_interleave(4, 0) + 1e-3 * torch.randn(32, d, generator=g)
+    gb = GalleryBank(bank)
+    s1, i1 = gb.topk(qs, 10, mode="tensor")
+    assert gb.last_stats["uncertified"] > 0
+    assert gb.retry_stats["second_pass"] > 0 and gb.retry_stats["exact"] == 0, gb.retry_stats
+    s2, i2 = gb.topk(qs, 10, mode="exact")
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    sess = gb.session(32, 10, vote=False)            # same completion after a graph replay
+    _, s3, i3 = sess.run(qs.cuda())
+    assert torch.equal(i3.cpu(), i2) and torch.equal(s3.cpu(), s2)
+
 
 # ------------------------------------------------------------------------------------ CUDA-graph sessions
 def test_session_replay_equals_eager_and_handles_fallback():
