@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", help="C1..C5 (synth.CONFIGS); default = BASELINE configs[1]")
-    ap.add_argument("--n", type=int, default=None, help="override gallery rows (total)")
+    ap.add_argument("--n", "--gallery-rows", dest="n", type=int, default=None,
+                    help="override gallery rows (total); spell it --gallery-rows under torchrun (--n is ambiguous there)")
     ap.add_argument("--q", type=int, default=None, help="override query batch")
     ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=None, help="queries in the CPU-baseline sample")

@@ -172,8 +172,10 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   }
   const int total = static_cast<int>(scratch[18]);
   // rows that are in no list score <= the threshold their list ended with (bf16 contraction)
-  float tprime = ord2f(scratch[19]);
+  // every gallery row is in some list (no threshold dropped anything): only the kc cut below
+  // separates rows from the re-score
   const bool all_in = (static_cast<int64_t>(total) == ng);
+  float tprime = all_in ? -INFINITY : ord2f(scratch[19]);
   if (!staged) {
     // fallback: streaming selection on the ordered similarity bits -- kBins linear bins over
     // [lo, hi], narrowed to the bin that holds the kc-th best until that bin fits the stage.
@@ -387,7 +389,8 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   __syncthreads();
   if (tid == 0) {
     const float sk = (nr >= k) ? __uint_as_float(scratch[7]) : -INFINITY;
-    const bool certified = (nr >= k) && (all_in || (tprime + eps < sk));
+    // rows outside `sel` score <= tprime in bf16 (list thresholds, kc cut), hence <= tprime + eps in fp32
+    const bool certified = (nr >= k) && (tprime + eps < sk);
     if (!certified) uncert_list[atomicAdd(uncert_count, 1)] = static_cast<int32_t>(q);
   }
 }

@@ -417,6 +417,19 @@ def test_kth_neighbour_matches_neg_sampler_static():
         assert same.float().mean() > 0.99
     assert torch.equal(metrics.kth_neighbour(emb, 1), torch.arange(256))  # rank 1 is the row itself
 
+@pytest.mark.parametrize("n,nq", [(8192, 256), (16384, 256), (8192, 64), (5000, 700)])
+def test_near_duplicate_gallery_never_certifies_on_list_completeness_alone(n, nq):
+    """Every row of a near-duplicate gallery passes any threshold, so the candidate lists can hold
+    the WHOLE gallery; that alone must not certify a query -- only kc rows reach the re-score."""
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1, 256, generator=g)
+    gb = GalleryBank(base + 1e-4 * torch.randn(n, 256, generator=g))
+    qd = base + 1e-4 * torch.randn(nq, 256, generator=g)
+    s1, i1 = gb.topk(qd, 10, mode="tensor")
+    s2, i2 = gb.topk(qd, 10, mode="exact")
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
 def test_uncertified_queries_are_finished_by_a_second_tensor_pass():
     """300 near-identical neighbours per query: the kc = 84 best bf16 candidates cannot certify the
     fp32 top-10, but the second pass (threshold = best-so-far k-th score - eps, kc x 4) collects the
