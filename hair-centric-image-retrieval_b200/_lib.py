@@ -48,6 +48,8 @@ SIGNATURES = {
     "hcir_exact_topk": (_INT, [_P, _P, _INT, _I64, _INT, _I64, _P, _I64, _P, _P, _P, C.c_size_t, _INT, _P]),
     "hcir_gather_labels": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
     "hcir_vote": (_INT, [_P, _P, _I64, _INT, _INT, _F, _P, _P, _P]),
+    "hcir_vote_idx": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _INT, _F, _P, _P, _P, _P]),
+    "hcir_vote_classes": (_INT, [_P, _P, _I64, _INT, _INT, _F, _P, _P, _P]),
     "hcir_merge_topk": (_INT, [_P, _P, _P, _INT, _I64, _INT, _P, _P, _P, _P]),
     "hcir_packed_block_bytes": (C.c_size_t, [_I64, _INT, _INT]),
     "hcir_merge_topk_packed": (_INT, [_P, _INT, _I64, _INT, _INT, C.c_size_t, _P, _P, _P, _P]),

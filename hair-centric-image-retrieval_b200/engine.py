@@ -360,6 +360,33 @@ class GalleryBank:
                                       scores.data_ptr() if return_scores else None, _stream_ptr()), "vote")
         return (pred, scores) if return_scores else pred
 
+    def vote_from_idx(self, sims: torch.Tensor, idx: torch.Tensor, *, T=None, nbr_out: torch.Tensor | None = None):
+        """Fused K4 tail on device tensors: neighbour-label gather -> vote -> ORIGINAL label value
+        [Q] int64 (one launch; ``nbr_out`` optionally receives the [Q, k] neighbour class indices)."""
+        if self.labels is None:
+            raise ValueError("this GalleryBank was built without labels")
+        nq, k = sims.shape
+        cls = self._classes_device()
+        pred = torch.empty((nq,), dtype=torch.int64, device=self.device)
+        self.launches += 1
+        _lib.check(self.lib.hcir_vote_idx(sims.data_ptr(), idx.data_ptr(), self.labels.data_ptr(), self.n,
+                                          self.idx_offset, nq, k, len(self.classes_),
+                                          float(T) if T is not None else 0.0, cls.data_ptr(), pred.data_ptr(),
+                                          nbr_out.data_ptr() if nbr_out is not None else None, _stream_ptr()),
+                   "vote_idx")
+        return pred
+
+    def vote_from_labels(self, sims: torch.Tensor, nbr_labels: torch.Tensor, *, T=None):
+        """K4 on gathered neighbour class indices -> ORIGINAL label value [Q] int64 (one launch)."""
+        nq, k = sims.shape
+        cls = self._classes_device()
+        pred = torch.empty((nq,), dtype=torch.int64, device=self.device)
+        self.launches += 1
+        _lib.check(self.lib.hcir_vote_classes(sims.data_ptr(), nbr_labels.data_ptr(), nq, k, len(self.classes_),
+                                              float(T) if T is not None else 0.0, cls.data_ptr(), pred.data_ptr(),
+                                              _stream_ptr()), "vote_classes")
+        return pred
+
     def predict(self, queries, k: int, *, T=None, mode: str = "auto", return_neighbors: bool = False):
         """kNN classification: predicted ORIGINAL label values [Q] int64.  ``T=None`` is the
         reference's uniform vote; ``T>0`` the temperature-weighted extension."""
@@ -369,10 +396,10 @@ class GalleryBank:
                 q = q.contiguous().to(self.device, non_blocking=True)
             elif q.device != self.device:
                 q = q.to(self.device)
-            cls = self._classes_device()
+            self._classes_device()
 
             def tail(s, i):
-                return cls[self.vote(s, self.neighbour_labels(i), T=T).long()]
+                return self.vote_from_idx(s, i, T=T)
 
             sims, idx, pred = self._search(q, int(k), mode, tail)
             if return_neighbors:
@@ -526,10 +553,10 @@ class SearchSession:
                                            self.unc_list.data_ptr(), self.unc_cnt.data_ptr(), st), "select_rescore")
         self._mark("t3", capture)
         kernels += 2
-        self.pred = self._tail() if self.vote else None
+        self.pred = self._tail() if self.vote else None   # (packed results: also fills out_lab)
         if self.vote:
-            kernels += 2
-        if self.out_lab is not None:
+            kernels += 1
+        elif self.out_lab is not None:
             self._gather_packed_labels()
             kernels += 1
         if self.trailer:
@@ -545,9 +572,7 @@ class SearchSession:
                                             b.idx_offset, self.out_lab.data_ptr(), _stream_ptr()), "gather_labels")
 
     def _tail(self):
-        b = self.bank
-        cls = b._classes_device()
-        return cls[b.vote(self.out_sim, b.neighbour_labels(self.out_idx), T=self.T).long()]
+        return self.bank.vote_from_idx(self.out_sim, self.out_idx, T=self.T, nbr_out=self.out_lab)
 
     def kernel_ms(self):
         """Durations (ms) of the profiled phases of the LAST replay (profile=True only)."""
@@ -587,7 +612,7 @@ class SearchSession:
                                       self.out_idx)
                 if self.vote:
                     pred = self._tail()
-                if self.out_lab is not None:
+                elif self.out_lab is not None:
                     self._gather_packed_labels()
             b.last_stats = {"path": "tensor+graph", "uncertified": n_unc, "nsplit": int(self.plan.nsplit),
                             "kc": int(self.plan.kc), "cap": int(self.plan.cap),

@@ -30,6 +30,42 @@ class _DeviceBytes:
                                          "version": 3, "strides": None}
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on EVERY rank of the group when any rank could not set the peer regions up."""
+
+
+def _all_ok(ok: bool, group, device) -> bool:
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
+
+
+def probe(group=None, device=None) -> bool:
+    """Collective self-test: one tiny channel, one exchanged step, contents checked on every rank.
+    True on all ranks or False on all ranks."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    try:
+        xc = PeerExchange(1024, group=group, device=device, timeout_s=2.0)
+    except PeerUnavailable:
+        return False
+    ok = True
+    try:
+        with torch.cuda.device(device):
+            blk = torch.full((1024,), xc.rank + 1, dtype=torch.uint8, device=device)
+            meta = torch.tensor([100 + xc.rank], dtype=torch.int32, device=device)
+            for _ in range(3):   # both parities
+                xc.exchange(blk, meta)
+                ok = ok and xc.metas() == [100 + r for r in range(xc.world)]
+                g = xc.gathered()[:, :1024]
+                want = torch.arange(1, xc.world + 1, dtype=torch.uint8, device=device)[:, None].expand(-1, 1024)
+                ok = ok and bool(torch.equal(g, want))
+    except RuntimeError:
+        ok = False
+    ok = _all_ok(ok, group, device)
+    xc.close()
+    return ok
+
+
 class PeerExchange:
     """One exchange channel: ``slot_bytes`` per rank and step.  Construction is COLLECTIVE over
     ``group`` (IPC handle all-gather + barrier) and must happen outside CUDA-graph capture."""
@@ -48,19 +84,36 @@ class PeerExchange:
         total = int(self.lib.hcir_peer_region_bytes(self.world, self.slot_bytes))
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.hcir_peer_alloc(total, C.byref(ptr), handle), "peer_alloc")
+            # every collective below is reached by every rank whatever failed locally, and a failure
+            # anywhere raises PeerUnavailable everywhere
+            why = None
+            rc = self.lib.hcir_peer_alloc(total, C.byref(ptr), handle)
+            if rc != 0:
+                why = f"peer_alloc: {_lib.last_error()}"
             handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            self._local_ptr = int(ptr.value)
+            dist.all_gather_object(handles, handle.raw if rc == 0 else None, group=group)
+            self._local_ptr = int(ptr.value) if rc == 0 else 0
             ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(self._local_ptr)
-                    continue
-                p = C.c_void_p()
-                _lib.check(self.lib.hcir_peer_open(C.create_string_buffer(handles[r], 64), C.byref(p)),
-                           f"peer_open(rank {r})")
-                ptrs.append(int(p.value))
+            if all(h is not None for h in handles):
+                for r in range(self.world):
+                    if r == self.rank:
+                        ptrs.append(self._local_ptr)
+                        continue
+                    p = C.c_void_p()
+                    if self.lib.hcir_peer_open(C.create_string_buffer(handles[r], 64), C.byref(p)) != 0:
+                        why = f"peer_open(rank {r}): {_lib.last_error()}"
+                        break
+                    ptrs.append(int(p.value))
+            else:
+                why = why or "a peer could not allocate / export its region"
+            if not _all_ok(why is None, group, self.device):
+                for r, p in enumerate(ptrs):
+                    if r != self.rank:
+                        self.lib.hcir_peer_close(p)
+                dist.barrier(group)
+                if self._local_ptr:
+                    self.lib.hcir_peer_free(self._local_ptr)
+                raise PeerUnavailable(f"rank {self.rank}: {why or 'a peer failed to map the regions'}")
             self._ptrs = ptrs
             self._regions = (C.c_void_p * self.world)(*ptrs)
             self._mem = _DeviceBytes(self._local_ptr, total)

@@ -18,11 +18,26 @@ import os
 
 from . import _lib
 from .engine import GalleryBank, _as_2d_f32, _stream_ptr, _to_host
+import warnings
+
+from . import peer as _peer
 from .peer import PeerExchange
 
 # how the per-rank result blocks travel: "peer" = the library's own push over NVLink peer memory
 # (csrc/peer.cu, captured into the step's CUDA graph), "nccl" = one ncclAllGather
-DEFAULT_EXCHANGE = os.environ.get("HCIR_EXCHANGE", "nccl")
+DEFAULT_EXCHANGE = os.environ.get("HCIR_EXCHANGE", "peer")
+
+
+def _resolve_exchange(exchange, group, device) -> str:
+    """"peer" needs CUDA IPC + P2P between all GPUs of the group: a collective self-test decides,
+    identically on every rank, whether the channel works; NCCL carries the blocks otherwise."""
+    exchange = exchange or DEFAULT_EXCHANGE
+    if exchange not in ("peer", "nccl"):
+        raise ValueError(f"unknown exchange {exchange!r}")
+    if exchange == "peer" and dist.get_world_size(group) > 1 and not _peer.probe(group, device):
+        warnings.warn("hcir_b200: peer-memory exchange unavailable on this box (CUDA IPC / P2P); using NCCL")
+        return "nccl"
+    return exchange
 
 
 @dataclass(frozen=True)
@@ -98,9 +113,6 @@ class ShardedGallery:
 
     def __init__(self, features_local, labels_local=None, *, n_total: int, group=None, device=None,
                  classes=None, exchange: str | None = None):
-        self.exchange = exchange or DEFAULT_EXCHANGE
-        if self.exchange not in ("peer", "nccl"):
-            raise ValueError(f"unknown exchange {self.exchange!r}")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -113,6 +125,7 @@ class ShardedGallery:
         self.bank = GalleryBank(feats, labels_local, device=device, idx_offset=self.plan.start(self.rank),
                                 classes=classes)
         self.device = self.bank.device
+        self.exchange = _resolve_exchange(exchange, group, self.device)
         self.profile = False       # bench.py: capture per-kernel events inside the graph
         self.last_session = None
 
@@ -155,7 +168,7 @@ class ShardedGallery:
                                             o_l.data_ptr() if has_lab else None, _stream_ptr()), "merge_topk_peer")
         pred = None
         if want_vote:
-            pred = self.bank._classes_device()[self.bank.vote(o_s, o_l, T=T).long()]
+            pred = self.bank.vote_from_labels(o_s, o_l, T=T)
         return {"gathered": None, "xchg": xc, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
 
     def _post_nccl(self, sess, want_vote: bool, T):
@@ -177,7 +190,7 @@ class ShardedGallery:
                                               _stream_ptr()), "merge_topk_packed")
         pred = None
         if want_vote:
-            pred = self.bank._classes_device()[self.bank.vote(o_s, o_l, T=T).long()]
+            pred = self.bank.vote_from_labels(o_s, o_l, T=T)
         return {"gathered": gathered, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
 
     def _step_packed(self, q: torch.Tensor, k: int, want_vote: bool, T):
@@ -287,14 +300,12 @@ class QueryShardedGallery:
     answered by exactly the single-GPU code path)."""
 
     def __init__(self, features, labels=None, *, group=None, device=None, classes=None, exchange: str | None = None):
-        self.exchange = exchange or DEFAULT_EXCHANGE
-        if self.exchange not in ("peer", "nccl"):
-            raise ValueError(f"unknown exchange {self.exchange!r}")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.bank = GalleryBank(features, labels, device=device, classes=classes)
         self.device = self.bank.device
+        self.exchange = _resolve_exchange(exchange, group, self.device)
         self.profile = False       # bench.py: capture per-kernel events inside the graph
         self.last_session = None
 

@@ -163,6 +163,20 @@ int hcir_gather_labels(const int64_t* idx, int64_t count, const int32_t* labels,
 int hcir_vote(const float* sims, const int32_t* nbr_labels, int64_t nq, int k, int num_classes,
               float T, int32_t* pred, float* scores, hcir_stream_t stream);
 
+/* K4, fused tail of the classification step: neighbour-label gather (idx are GLOBAL row indices,
+ * labels the local [n_labels] class-index vector, idx_offset the first local row) -> vote -> class
+ * value.  pred[q] = classes[best] (or the class index when classes is null), int64 like sklearn's
+ * predict.  nbr_labels_out (nullable) receives the gathered [nq, k] neighbour labels.  Same
+ * arithmetic and tie rule as hcir_gather_labels + hcir_vote. */
+int hcir_vote_idx(const float* sims, const int64_t* idx, const int32_t* labels, int64_t n_labels,
+                  int64_t idx_offset, int64_t nq, int k, int num_classes, float T,
+                  const int64_t* classes, int64_t* pred, int32_t* nbr_labels_out,
+                  hcir_stream_t stream);
+/* the same vote on already gathered neighbour labels (multi-GPU: they travel with the candidates) */
+int hcir_vote_classes(const float* sims, const int32_t* nbr_labels, int64_t nq, int k,
+                      int num_classes, float T, const int64_t* classes, int64_t* pred,
+                      hcir_stream_t stream);
+
 /* K5 -- merge of per-shard exact top-k lists after the all-gather (new design, no reference
  * analogue).  gathered_* are [G][nq][k] with every [g][q][:] list in
  * canonical order; output the canonical top-k of the union.  Labels are optional. */
