@@ -454,6 +454,31 @@ def knn_predict(query, bank, labels, k, *, T=None, mode: str = "auto"):
 
 
 # ---------------------------------------------------------------------------------------------
+# pipelined submission: the host-side check of a step is deferred behind the next step's launch
+# ---------------------------------------------------------------------------------------------
+class PendingStep:
+    """A submitted search step.  The device work is enqueued; the few bytes that decide whether
+    the (rare) uncertified completion is needed travel to pinned host memory asynchronously and are
+    looked at only in ``result()`` -- so a caller that keeps one or two steps in flight (submit the
+    next, then take the previous result) never leaves the GPU idle on a host round trip.
+    ``result()`` returns the step's exact results (device tensors owned by the caller)."""
+
+    def __init__(self, event, flags_host, needs_redo, results, redo):
+        self._event, self._flags, self._needs_redo, self._results, self._redo = event, flags_host, needs_redo, results, redo
+        self.redone = False
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+            if self._needs_redo(self._flags):
+                self._results = self._redo()
+                self.redone = True
+            self._redo = self._needs_redo = None
+        return self._results
+
+
+# ---------------------------------------------------------------------------------------------
 # CUDA-graph session: one fixed-shape predict / top-k step replayed with a single launch
 # ---------------------------------------------------------------------------------------------
 class SearchSession:
@@ -590,6 +615,39 @@ class SearchSession:
         b._finish_uncertified(self.q32, self.qbf, self.qdl, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
         if self.out_lab is not None:
             self._gather_packed_labels()
+
+    def submit(self, queries) -> PendingStep:
+        """Pipelined ``run``: enqueue the step and return at once.  ``result()`` of the returned
+        handle gives (pred | None, sims, idx) as fresh device tensors; uncertified queries (rare) are
+        completed there by re-running this batch through the eager path.  ``queries`` must stay
+        unmodified until then.  At most 8 steps may be pending per session."""
+        b = self.bank
+        if tuple(queries.shape) != (self.nq, b.d):
+            raise ValueError(f"session was built for queries of shape {(self.nq, b.d)}, got {tuple(queries.shape)}")
+        with torch.cuda.device(b.device):
+            ring = self.__dict__.get("_flag_ring")
+            if ring is None:
+                ring = self._flag_ring = torch.zeros((8, 1), dtype=torch.int32, pin_memory=True)
+                self._submitted = 0
+            slot = ring[self._submitted % 8]
+            self._submitted += 1
+            self.q_in.copy_(queries, non_blocking=True)
+            self.graph.replay()
+            b.launches += self.kernels_per_run
+            res = (self.pred.clone() if self.pred is not None else None, self.out_sim.clone(), self.out_idx.clone())
+            slot.copy_(self.unc_cnt, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+
+        def redo():
+            with torch.cuda.device(b.device):
+                q = queries if queries.is_cuda else queries.to(b.device)
+                if self.vote:
+                    return b.predict(q, self.k, T=self.T, mode="tensor", return_neighbors=True)
+                s_, i_ = b._topk_device(q, self.k, "tensor")
+                return None, s_, i_
+
+        return PendingStep(ev, slot, lambda f: int(f[0]) > 0, res, redo)
 
     def run(self, queries, check: bool = True):
         """queries: [nq, d] fp32 tensor (device, or host -- pinned for an async copy).  Returns

@@ -170,6 +170,26 @@ class PeerExchange:
             raise RuntimeError(f"peer exchange: device step {int(h[_HDR_STEP])} != host step {self.host_step}")
         return h
 
+    def header_async(self):
+        """Enqueue the header read of the step just issued into a pinned slot (ring of 8); returns
+        (slot, step) for ``metas_of`` once the caller has synchronised with the stream."""
+        ring = self.__dict__.get("_hdr_ring")
+        if ring is None:
+            ring = self._hdr_ring = torch.zeros((8, _HDR_WORDS), dtype=torch.int64, pin_memory=True)
+        slot = ring[self.host_step % 8]
+        slot.copy_(self.local[: _HDR_WORDS * 8].view(torch.int64), non_blocking=True)
+        return slot, self.host_step
+
+    def metas_of(self, slot: torch.Tensor, step: int) -> list[int]:
+        h = slot.numpy()
+        if h[_HDR_ERR] != 0:
+            raise RuntimeError(f"peer exchange: rank {self.rank} timed out waiting for a peer's block at step "
+                               f"{int(h[_HDR_ERR])}")
+        if int(h[_HDR_STEP]) != step:
+            raise RuntimeError(f"peer exchange: device step {int(h[_HDR_STEP])} != host step {step}")
+        par = step & 1
+        return [int(v) for v in h[_HDR_META + par * _PEER_MAX: _HDR_META + par * _PEER_MAX + self.world]]
+
     def metas(self, header: np.ndarray | None = None) -> list[int]:
         h = self.header() if header is None else header
         par = self.host_step & 1

@@ -17,7 +17,7 @@ import torch.distributed as dist
 import os
 
 from . import _lib
-from .engine import GalleryBank, _as_2d_f32, _stream_ptr, _to_host
+from .engine import GalleryBank, PendingStep, _as_2d_f32, _stream_ptr, _to_host
 import warnings
 
 from . import peer as _peer
@@ -222,6 +222,34 @@ class ShardedGallery:
                                 "chunk_w": int(sess.plan.chunk_w)}
         return out
 
+    def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:
+        """Pipelined ``predict`` for DEVICE queries (peer exchange only; anything else completes
+        synchronously inside this call): the step is enqueued, the header of the peer region that
+        carries every rank's uncertified count is read back asynchronously, and ``result()`` -> pred
+        [Q] int64 on the device decides -- identically on every rank -- whether the batch has to be
+        redone through the synchronous path.  Up to two steps may be in flight (the peer regions are
+        double-buffered)."""
+        q, kind = _as_2d_f32(queries, "queries")
+        ok = (self.exchange == "peer" and q.is_cuda and q.shape[0] > 0 and self.bank.labels is not None and all(
+            GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world)))
+        if ok:
+            with torch.cuda.device(self.device):
+                key = ("gallery-sharded", self.exchange, True, None if T is None else float(T))
+                sess = self.bank.session(q.shape[0], int(k), vote=False, profile=self.profile, pack=True,
+                                         post=lambda s_: self._post(s_, True, T), post_key=key)
+                if sess is not None and sess.out_lab is not None:
+                    sess.run(q, check=False)
+                    self.last_session = sess
+                    xc = sess.post_out["xchg"]
+                    xc.note_replay()
+                    slot, step = xc.header_async()
+                    pred = sess.post_out["pred"].clone()
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), pred,
+                                       lambda: self.predict(q, k, T=T))
+        return PendingStep(None, None, None, self.predict(queries, k, T=T), None)
+
     def topk(self, queries, k: int, *, mode: str = "auto", with_labels: bool = False):
         q, kind = _as_2d_f32(queries, "queries")
         with torch.cuda.device(self.device):
@@ -330,8 +358,9 @@ class QueryShardedGallery:
         xc.exchange(blk.view(torch.uint8), meta=sess.unc_cnt)
         return {"xchg": xc}
 
-    def _predict_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
-        """Whole step = one graph launch per rank incl. the result exchange; None if not applicable."""
+    def _issue_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
+        """Enqueue the whole step (one graph launch per rank incl. the result exchange); None if the
+        tensor path does not apply.  -> (session, exchange, sizes, hmax)"""
         sizes = [sp.size(r) for r in range(self.world)]
         if min(sizes) < 1 or not self.bank.use_tensor_path(mine.shape[0], k):   # same decision on every rank
             return None
@@ -344,6 +373,37 @@ class QueryShardedGallery:
         self.last_session = sess
         xc = sess.post_out["xchg"]
         xc.note_replay()
+        return sess, xc, sizes, hmax
+
+    def _gathered_preds(self, xc, sizes, hmax) -> torch.Tensor:
+        g = xc.gathered()[:, : hmax * 8]
+        if all(sz == hmax for sz in sizes) and xc.stride == hmax * 8:
+            return g.reshape(-1).view(torch.int64).clone()   # the region is reused two steps later
+        return torch.cat([g[r, : sizes[r] * 8].contiguous().view(torch.int64) for r in range(self.world)], 0)
+
+    def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:
+        """Pipelined ``predict`` for DEVICE queries (see ShardedGallery.submit_predict)."""
+        q, kind = _as_2d_f32(queries, "queries")
+        if self.exchange == "peer" and q.is_cuda:
+            sp, mine = self._slice(q)
+            with torch.cuda.device(self.device):
+                issued = self._issue_peer(mine, sp, int(k), T)
+                if issued is not None:
+                    sess, xc, sizes, hmax = issued
+                    slot, step = xc.header_async()
+                    pred = self._gathered_preds(xc, sizes, hmax)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), pred,
+                                       lambda: self.predict(q, k, T=T))
+        return PendingStep(None, None, None, self.predict(queries, k, T=T), None)
+
+    def _predict_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
+        """Whole step = one graph launch per rank incl. the result exchange; None if not applicable."""
+        issued = self._issue_peer(mine, sp, k, T)
+        if issued is None:
+            return None
+        sess, xc, sizes, hmax = issued
         counts = xc.metas()
         self.bank.last_stats = {"path": "tensor+graph", "uncertified": int(sum(counts)),
                                 "nsplit": int(sess.plan.nsplit), "kc": int(sess.plan.kc), "cap": int(sess.plan.cap),
@@ -355,10 +415,7 @@ class QueryShardedGallery:
                 sess.finish_uncertified(counts[self.rank])
                 pred = sess._tail()
             return self._gather_rows(pred, sp)
-        g = xc.gathered()[:, : hmax * 8]
-        if all(sz == hmax for sz in sizes) and xc.stride == hmax * 8:
-            return g.reshape(-1).view(torch.int64).clone()   # the region is reused two steps later
-        return torch.cat([g[r, : sizes[r] * 8].contiguous().view(torch.int64) for r in range(self.world)], 0)
+        return self._gathered_preds(xc, sizes, hmax)
 
     def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
         q, kind = _as_2d_f32(queries, "queries")

@@ -52,6 +52,13 @@ def main():
                 assert torch.equal(p, p_ref), (tag, exchange, "query predict", rep)
                 p = qg.predict(qs.cuda(), k)
                 assert torch.equal(p.cpu(), p_ref), (tag, exchange, "query predict (device queries)", rep)
+            if exchange == "peer":   # pipelined submission: two steps in flight, checks read one step late
+                qc = qs.cuda()
+                for obj in (gal, qg):
+                    pend = [obj.submit_predict(qc, k), obj.submit_predict(qc, k)]
+                    for h in pend:
+                        assert torch.equal(h.result().cpu(), p_ref), (tag, "submit_predict", type(obj).__name__)
+                        assert h.redone == bool(expect_uncertified), (tag, "redone", type(obj).__name__)
             checks += 1
             del gal, qg
         del ref

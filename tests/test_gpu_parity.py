@@ -451,6 +451,30 @@ def test_uncertified_queries_are_finished_by_a_second_tensor_pass():
     assert torch.equal(i3.cpu(), i2) and torch.equal(s3.cpu(), s2)
 
 
+def test_pipelined_submit_result_equals_run_and_redoes_uncertified_batches():
+    bank, bl = synth.make_clustered(30000, 256, 27, 61)
+    gb = GalleryBank(bank, bl)
+    sess = gb.session(300, 20)
+    batches = [synth.make_clustered(300, 256, 27, 70 + i)[0].cuda() for i in range(4)]
+    pend = [sess.submit(b) for b in batches[:2]]            # two steps in flight
+    got = [pend[0].result()]
+    pend.append(sess.submit(batches[2]))
+    got += [pend[1].result(), pend[2].result()]
+    for b, (p, s_, i_) in zip(batches, got):
+        p_ref, s_ref, i_ref = gb.predict(b, 20, return_neighbors=True)
+        assert torch.equal(p, p_ref) and torch.equal(s_, s_ref) and torch.equal(i_, i_ref)
+    assert not any(x.redone for x in pend)
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1, 256, generator=g)
+    dup = GalleryBank(base + 1e-4 * torch.randn(8192, 256, generator=g), torch.arange(8192) % 5)
+    qd = (base + 1e-4 * torch.randn(64, 256, generator=g)).cuda()
+    h = dup.session(64, 10).submit(qd)
+    p, s_, i_ = h.result()
+    assert h.redone
+    s2, i2 = dup.topk(qd, 10, mode="exact")
+    assert torch.equal(i_, i2) and torch.equal(s_, s2) and torch.equal(p, dup.predict(qd, 10, mode="exact"))
+
+
 # ------------------------------------------------------------------------------------ CUDA-graph sessions
 def test_session_replay_equals_eager_and_handles_fallback():
     bank, bl = synth.make_clustered(30000, 768, 27, 61)
