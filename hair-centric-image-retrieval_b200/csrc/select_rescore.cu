@@ -10,8 +10,9 @@
 
 namespace hcir {
 
-constexpr int kSelThreads = 256;
-constexpr int kSelWarps = kSelThreads / kWarp;
+// CTA width is a template parameter: 256 threads x 5 CTAs/SM in general, 128 threads x 10 CTAs/SM for
+// small k and many queries (measured on C2, k=20: 0.45 -> 0.40 ms -- twice as many queries in flight hide
+// the barrier / gather latencies -- while k=100/200 and the 64-query streaming regime lose 40-60 %).
 constexpr int kRound1Slack = 6;
 constexpr int kBins = 2048;  // histogram bins of the fallback streaming selection
 
@@ -40,9 +41,10 @@ static SelSmem sel_smem_layout(int nlists, int kc, int ld) {
 // list (coalesced 256-byte reads), kKeyBatch loads in flight per lane before any is consumed
 // (the visitor has shared-memory side effects the compiler will not hoist loads across).
 constexpr int kKeyBatch = 8;
-template <typename F>
+template <int kSelThreads, typename F>
 __device__ __forceinline__ void for_each_key(const uint64_t* __restrict__ lists, const int32_t* cnts, int nlists,
                                              int cap, int warp, int lane, F&& f) {
+  constexpr int kSelWarps = kSelThreads / kWarp;
   for (int s = warp; s < nlists; s += kSelWarps) {
     const int c = cnts[s];
     const uint64_t* src = lists + static_cast<int64_t>(s) * cap;
@@ -62,6 +64,7 @@ __device__ __forceinline__ void for_each_key(const uint64_t* __restrict__ lists,
 
 // rank (number of strictly greater keys) of every key[0..n) -> dst[rank] = key for rank < keep.
 // Keys are unique, so ranks are a permutation.  The caller syncs.
+template <int kSelThreads>
 __device__ __forceinline__ void rank_scatter(const uint64_t* keys, int n, uint64_t* dst, int keep, int tid) {
   for (int j = tid; j < n; j += kSelThreads) {
     const uint64_t mine = keys[j];
@@ -71,7 +74,8 @@ __device__ __forceinline__ void rank_scatter(const uint64_t* keys, int n, uint64
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 5)
+template <int kSelThreads>
+__global__ void __launch_bounds__(kSelThreads, 1280 / kSelThreads)
 select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int ld, int64_t nq,
                       int64_t ng, int k, int64_t idx_offset, int nlists, int cap, int kc,
                       const int32_t* __restrict__ counts, const uint64_t* __restrict__ cand,
@@ -79,6 +83,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
                       const float* __restrict__ q_delta, float g_delta_max, float eps_acc,
                       float* __restrict__ out_sim, int64_t* __restrict__ out_idx,
                       int32_t* __restrict__ uncert_list, int32_t* __restrict__ uncert_count, SelSmem L) {
+  constexpr int kSelWarps = kSelThreads / kWarp;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw + L.stage);
   uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw + L.sel);   // kc best by bf16 score, DESCENDING
@@ -149,7 +154,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   int nstage = 0;
   bool staged = false;
   {
-    for_each_key(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
+    for_each_key<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
       if (static_cast<uint32_t>(key >> 32) > hint) {
         const uint32_t at = atomicAdd(&scratch[9], 1u);
         if (at < static_cast<uint32_t>(L.stage_cap)) stage[at] = key;
@@ -193,7 +198,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       while ((span >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
       for (int b = tid; b < kBins; b += kSelThreads) hist[b] = 0;
       __syncthreads();
-      for_each_key(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
+      for_each_key<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
         const uint32_t o = static_cast<uint32_t>(key >> 32);
         if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
         else if (check_range) scratch[13] = 1u;
@@ -245,7 +250,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     }
     // collect everything at or above the cut (exact ties beyond the staging room are dropped:
     // they score == the kc-th best, which the certification bound below covers)
-    for_each_key(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
+    for_each_key<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
       if (static_cast<uint32_t>(key >> 32) >= cut) {
         const uint32_t at = atomicAdd(&scratch[9], 1u);
         if (at < static_cast<uint32_t>(L.stage_cap)) stage[at] = key;
@@ -326,7 +331,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       npool = keep;
     }
   }
-  rank_scatter(pool, npool, sel, kc, tid);
+  rank_scatter<kSelThreads>(pool, npool, sel, kc, tid);
   __syncthreads();
   if (nstage > kc) tprime = fmaxf(tprime, key_sim(sel[kc - 1]));
 
@@ -416,16 +421,22 @@ extern "C" int hcir_select_rescore(const float* q_f32, const float* g_f32, int l
   const SelSmem L = sel_smem_layout(plan->nlists, plan->kc, ld);
   HCIR_REQUIRE(L.total <= 220 * 1024, "select_rescore: kc=%d ld=%d needs %zu B of shared memory", plan->kc, ld,
                L.total);
-  HCIR_CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(L.total)));
+  const bool narrow = (k <= 32 && nq >= 2048);
+  HCIR_CUDA_TRY(cudaFuncSetAttribute(narrow ? select_rescore_kernel<128> : select_rescore_kernel<256>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
   const char* ws = static_cast<const char*>(workspace);
   const int32_t* counts = reinterpret_cast<const int32_t*>(ws + plan->counts_off);
   const uint64_t* cand = reinterpret_cast<const uint64_t*>(ws + plan->keys_off);
   const float* thr_out = reinterpret_cast<const float*>(ws + plan->thr_out_off);
   const float* thr_hi = plan->sample_rows > 0 ? reinterpret_cast<const float*>(ws + plan->thr_hi_off) : nullptr;
-  select_rescore_kernel<<<static_cast<unsigned>(nq), kSelThreads, L.total, static_cast<cudaStream_t>(stream)>>>(
-      q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi,
-      q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
+  if (narrow)
+    select_rescore_kernel<128><<<static_cast<unsigned>(nq), 128, L.total, static_cast<cudaStream_t>(stream)>>>(
+        q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi,
+        q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
+  else
+    select_rescore_kernel<256><<<static_cast<unsigned>(nq), 256, L.total, static_cast<cudaStream_t>(stream)>>>(
+        q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi,
+        q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
   HCIR_CUDA_TRY(cudaGetLastError());
   return HCIR_OK;
 }
