@@ -128,3 +128,48 @@ def test_classifier_argument_validation():
         KNeighborsClassifierB200(5, weights="distance")
     with pytest.raises(RuntimeError):
         KNeighborsClassifierB200(5).predict(np.zeros((2, 4), np.float32))
+
+
+def test_peer_region_layout_and_argument_validation():
+    """Host-only arithmetic of the peer-memory exchange (csrc/peer.cu): header + 2 parities x world
+    slots, slots 256-byte aligned, push CTA count a pure function of the block size."""
+    lib = _lib.load()
+    for world, slot in [(2, 1024), (8, 10000 * 20 * 16), (8, 16), (16, 4097)]:
+        stride = -(-slot // 256) * 256
+        assert lib.hcir_peer_region_bytes(world, slot) == 512 + 2 * world * stride
+        seen = set()
+        for par in (0, 1):
+            for r in range(world):
+                off = lib.hcir_peer_slot_offset(world, slot, par, r)
+                assert off >= 512 and off % 256 == 0 and off + stride <= lib.hcir_peer_region_bytes(world, slot)
+                seen.add(off)
+        assert len(seen) == 2 * world
+    assert lib.hcir_peer_region_bytes(17, 1024) == 0 and lib.hcir_peer_region_bytes(0, 1024) == 0
+    assert lib.hcir_peer_push_ctas(16) == 1 and lib.hcir_peer_push_ctas(1 << 30) == 64
+    assert 1 <= lib.hcir_peer_push_ctas(10000 * 8) <= 64
+    # null pointers / bad ranks are rejected before any CUDA call
+    assert lib.hcir_peer_push(None, 16, None, 2, 0, 16, None, None, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_peer_wait(None, 2, None, 1, 0, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_merge_topk_peer(None, 2, 4, 3, 1, 1024, None, None, None, None, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_vote_idx(None, None, None, 4, 0, 4, 0, 3, 0.0, None, None, None, None) == _lib.HCIR_EINVAL
+
+
+def test_pending_step_defers_the_check_and_redoes_once():
+    from hcir_b200.engine import PendingStep
+
+    class Ev:
+        def __init__(self):
+            self.synced = 0
+
+        def synchronize(self):
+            self.synced += 1
+
+    ev, calls = Ev(), []
+    ok = PendingStep(ev, [0], lambda f: f[0] > 0, "fast", lambda: calls.append(1) or "redone")
+    assert ev.synced == 0                       # nothing is looked at before result()
+    assert ok.result() == "fast" and ok.result() == "fast" and ev.synced == 1 and not ok.redone and not calls
+    ev2 = Ev()
+    bad = PendingStep(ev2, [3], lambda f: f[0] > 0, "fast", lambda: calls.append(1) or "redone")
+    assert bad.result() == "redone" and bad.result() == "redone" and bad.redone and calls == [1]
+    done = PendingStep(None, None, None, "sync", None)   # a step that completed synchronously
+    assert done.result() == "sync" and not done.redone
