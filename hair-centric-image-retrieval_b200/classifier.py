@@ -41,6 +41,17 @@ class KNeighborsClassifierB200:
         self.n_features_in_ = self._bank.d
         return self
 
+    def fit_bank(self, bank: GalleryBank):
+        """``fit`` on a bank that is already on the device (``FeatureBankBuilder.finish()``: the
+        encoder loop of classification_engine.py:42-53 without the per-batch ``.cpu()``)."""
+        if bank.labels is None:
+            raise ValueError("fit_bank needs a GalleryBank with labels")
+        self._bank = bank
+        self.classes_ = bank.classes_
+        self.n_samples_fit_ = bank.n
+        self.n_features_in_ = bank.d
+        return self
+
     def _check(self):
         if self._bank is None:
             raise RuntimeError("This KNeighborsClassifierB200 instance is not fitted yet")

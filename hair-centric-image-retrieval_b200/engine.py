@@ -434,6 +434,109 @@ class GalleryBank:
 
 
 # ---------------------------------------------------------------------------------------------
+# encoder -> bank without leaving the device
+# ---------------------------------------------------------------------------------------------
+class FeatureBankBuilder:
+    """Device-side replacement of the feature-bank loop of ``Classifier.extracting_features``
+    (HairPretraining/src/classification_engine.py:42-53 and :66-67: per batch ``F.normalize`` on
+    the GPU, ``.cpu()``, and one ``torch.cat`` at the end).  ``append`` takes the encoder's
+    [B, D] output where it is -- on the device, un-normalised, fp32 / fp16 / bf16 -- and K1 writes
+    the unit fp32 and bf16 rows straight into the growing bank: no per-batch D2H sync, no host
+    copy, no concatenation, no second normalisation pass at ``fit``.  ``finish()`` returns the
+    :class:`GalleryBank` (bit-identical to ``GalleryBank(torch.cat(batches), labels)``)."""
+
+    def __init__(self, d: int, *, capacity: int = 1 << 16, device=None, idx_offset: int = 0):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.d = int(d)
+        self.ld = self.lib.hcir_padded_dim(self.d)
+        self.idx_offset = int(idx_offset)
+        self.n = 0
+        self._labels = []
+        with torch.cuda.device(self.device):
+            self._alloc(max(1, int(capacity)))
+            self._dmax = torch.zeros((), dtype=torch.float32, device=self.device)
+
+    def _alloc(self, cap: int):
+        g32 = torch.empty((cap, self.ld), dtype=torch.float32, device=self.device)
+        gbf = torch.empty((cap, self.ld), dtype=torch.bfloat16, device=self.device)
+        if self.n:
+            g32[: self.n].copy_(self.g32[: self.n])
+            gbf[: self.n].copy_(self.gbf[: self.n])
+        self.g32, self.gbf, self.capacity = g32, gbf, cap
+
+    def append(self, features: torch.Tensor, labels=None):
+        """features: [B, D] CUDA tensor (the encoder output of one batch); labels: [B] ints (any
+        device / numpy / list), kept on the host like the reference keeps them."""
+        if not isinstance(features, torch.Tensor) or not features.is_cuda or features.dim() != 2:
+            raise ValueError("FeatureBankBuilder.append expects a 2-D CUDA tensor [batch, dim]")
+        if features.shape[1] != self.d:
+            raise ValueError(f"feature dim {features.shape[1]} != builder dim {self.d}")
+        b = int(features.shape[0])
+        if labels is not None:
+            y = labels.detach().cpu().numpy() if isinstance(labels, torch.Tensor) else np.asarray(labels)
+            if y.reshape(-1).shape[0] != b:
+                raise ValueError(f"{y.reshape(-1).shape[0]} labels for {b} feature rows")
+            self._labels.append(y.reshape(-1))
+        elif self._labels:
+            raise ValueError("labels were given for earlier batches but not for this one")
+        if b == 0:
+            return self
+        with torch.cuda.device(self.device):
+            x = features.detach()
+            if x.device != self.device:
+                x = x.to(self.device)
+            if x.dtype != torch.float32:
+                x = x.float()
+            if x.stride(1) != 1:
+                x = x.contiguous()
+            if self.n + b > self.capacity:
+                self._alloc(max(self.n + b, 2 * self.capacity))
+            dl = torch.empty((b,), dtype=torch.float32, device=self.device)
+            a = self.n
+            _lib.check(self.lib.hcir_l2norm_cast(x.data_ptr(), b, self.d, x.stride(0), self.g32[a:a + b].data_ptr(),
+                                                 self.gbf[a:a + b].data_ptr(), self.ld, dl.data_ptr(), _stream_ptr()),
+                       "l2norm_cast")
+            self._dmax = torch.maximum(self._dmax, dl.max())
+            self.n += b
+        return self
+
+    def finish(self, classes=None) -> "GalleryBank":
+        if self.n == 0:
+            raise ValueError("FeatureBankBuilder.finish: no rows were appended")
+        labels = np.concatenate(self._labels) if self._labels else None
+        if labels is not None and labels.shape[0] != self.n:
+            raise ValueError("some batches were appended without labels")
+        return GalleryBank._from_parts(self.g32[: self.n], self.gbf[: self.n], float(self._dmax.item()), self.d,
+                                       labels, classes, self.device, self.idx_offset)
+
+
+def _gallery_from_parts(cls, g32, gbf, g_delta_max, d, labels, classes, device, idx_offset=0):
+    """A GalleryBank over already normalised device rows (FeatureBankBuilder.finish)."""
+    self = cls.__new__(cls)
+    self.lib = _lib.load()
+    self.device = device
+    self.n, self.d = int(g32.shape[0]), int(d)
+    self.ld = int(g32.shape[1])
+    self.idx_offset = int(idx_offset)
+    self.sm_count = _sm_count(device)
+    self.g32, self.gbf, self.g_delta_max = g32, gbf, float(g_delta_max)
+    self.eps_acc = float(self.ld) * 2.0 ** -22
+    self.labels = None
+    self.classes_ = None
+    self._cls_dev = None
+    if labels is not None:
+        self.set_labels(labels, classes)
+    self.last_stats, self.retry_stats = {}, {}
+    self.kernel_events = None
+    self.launches = 0
+    return self
+
+
+GalleryBank._from_parts = classmethod(_gallery_from_parts)
+
+
+# ---------------------------------------------------------------------------------------------
 # functional surface
 # ---------------------------------------------------------------------------------------------
 def knn_topk(bank, query, k, *, mode: str = "auto"):

@@ -475,6 +475,34 @@ def test_pipelined_submit_result_equals_run_and_redoes_uncertified_batches():
     assert torch.equal(i_, i2) and torch.equal(s_, s2) and torch.equal(p, dup.predict(qd, 10, mode="exact"))
 
 
+def test_feature_bank_builder_equals_concatenate_then_fit():
+    """classification_engine.py:42-53,66-67 without the per-batch .cpu(): batches appended on the
+    device (fp32 and fp16 encoder outputs, a growth step, an empty batch) give the very bank that
+    GalleryBank(torch.cat(batches)) builds, hence identical predictions."""
+    from hcir_b200 import FeatureBankBuilder
+    feats, labels = synth.make_clustered(9000, 512, 27, 81)
+    labels = labels * 2 + 2                                       # non-contiguous label values
+    sizes = [256, 256, 0, 1000, 3000, 4488]
+    fb = FeatureBankBuilder(512, capacity=1024)
+    a = 0
+    for sz in sizes:
+        fb.append(feats[a:a + sz].cuda(), labels[a:a + sz])
+        a += sz
+    bank = fb.finish()
+    ref = GalleryBank(feats, labels)
+    assert bank.n == 9000 and torch.equal(bank.g32, ref.g32) and torch.equal(bank.gbf, ref.gbf)
+    assert bank.g_delta_max == ref.g_delta_max and np.array_equal(bank.classes_, ref.classes_)
+    qs, _ = synth.make_clustered(500, 512, 27, 82)
+    clf = KNeighborsClassifierB200(20).fit_bank(bank)
+    np.testing.assert_array_equal(clf.predict(qs.numpy()), KNeighborsClassifierB200(20).fit(feats, labels.numpy()).predict(qs.numpy()))
+    half = FeatureBankBuilder(512).append(feats[:100].cuda().half(), labels[:100]).finish()   # AMP encoder output
+    assert torch.equal(half.g32, GalleryBank(feats[:100].half().float()).g32)
+    with pytest.raises(ValueError):
+        FeatureBankBuilder(512).append(feats[:4], labels[:4])     # host tensor: the point is to stay on the device
+    with pytest.raises(ValueError):
+        FeatureBankBuilder(256).append(feats[:4].cuda())
+
+
 # ------------------------------------------------------------------------------------ CUDA-graph sessions
 def test_session_replay_equals_eager_and_handles_fallback():
     bank, bl = synth.make_clustered(30000, 768, 27, 61)
