@@ -792,7 +792,10 @@ def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: 
     s = cache.get(key)
     if s is None:
         if len(cache) >= 4:  # each session owns a workspace: keep a handful
-            cache.pop(next(iter(cache)))
+            old = cache.pop(next(iter(cache)))
+            xc = getattr(old, "xchg", None)
+            if xc is not None:   # multi-GPU: every rank evicts the same session at the same call -> collective close
+                xc.close()
         s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack, post=post)
     return s
 

@@ -77,6 +77,15 @@ def main():
     qd = base + 1e-4 * torch.randn(256, 256, generator=g)
     case(dup, torch.arange(nd) % 5, qd, 10, "near-duplicates", expect_uncertified=True)
 
+    # more shapes than the session cache holds: evicted sessions close their peer regions collectively
+    ref = hcir_b200.GalleryBank(bank, bl, device=dev)
+    sp = ShardPlan(bank.shape[0], world)
+    gal = ShardedGallery(bank[sp.start(rank):sp.stop(rank)], bl[sp.start(rank):sp.stop(rank)], n_total=bank.shape[0],
+                         device=dev, classes=ref.classes_, exchange="peer")
+    for nq in (129, 130, 131, 132, 133, 134):
+        assert torch.equal(gal.predict(qs[:nq], 20), ref.predict(qs[:nq], 20)), ("eviction", nq)
+    checks += 1
+
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
