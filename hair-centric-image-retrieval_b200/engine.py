@@ -627,7 +627,7 @@ class SearchSession:
             mode = "thread_local" if post is not None else "global"
             with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self._body(capture=True)
-        self.launches_per_run = 1 + 0  # one graph launch; the kernels inside: self.kernels_per_run
+        self.launches_per_run = 1  # one graph launch; the kernels inside: self.kernels_per_run
 
     def _mark(self, name, capture):
         if not (capture and self._profile):
