@@ -11,6 +11,7 @@ section 8e "later fusion"; no reference analogue -- the reference's kNN is singl
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -70,7 +71,7 @@ class PeerExchange:
     """One exchange channel: ``slot_bytes`` per rank and step.  Construction is COLLECTIVE over
     ``group`` (IPC handle all-gather + barrier) and must happen outside CUDA-graph capture."""
 
-    def __init__(self, slot_bytes: int, *, group=None, device=None, timeout_s: float = 5.0):
+    def __init__(self, slot_bytes: int, *, group=None, device=None, timeout_s: float | None = None):
         self.lib = _lib.load()
         self.group = group
         self.world = dist.get_world_size(group)
@@ -80,6 +81,10 @@ class PeerExchange:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.slot_bytes = int(-(-int(slot_bytes) // 16) * 16)
         self.stride = -(-self.slot_bytes // 256) * 256
+        # how long a wait kernel spins for a late peer before it reports instead of hanging the GPU
+        # (ranks of one job reach the same step seconds apart at most; HCIR_PEER_TIMEOUT_S overrides)
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("HCIR_PEER_TIMEOUT_S", "30"))
         self.timeout_ns = int(timeout_s * 1e9)
         total = int(self.lib.hcir_peer_region_bytes(self.world, self.slot_bytes))
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
