@@ -186,7 +186,8 @@ def test_real27_golden_k_sweep(golden_dir):
 
 @pytest.mark.parametrize("mode", ["exact", "tensor"])
 @pytest.mark.parametrize("n,d,q,k", [(5000, 100, 33, 7), (4099, 768, 129, 20), (9000, 512, 1, 1),
-                                     (12000, 256, 260, 100), (6000, 64, 50, 642)])
+                                     (12000, 256, 260, 100), (6000, 64, 50, 642),
+                                     (30000, 2048, 300, 200), (8000, 2048, 40, 50)])   # C5's width and k
 def test_random_shapes(mode, n, d, q, k):
     bank, _ = synth.make_clustered(n, d, 13, 5 + n)
     qs, _ = synth.make_clustered(q, d, 13, 6 + n)
