@@ -53,9 +53,24 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile every csrc/*.cu for sm_100a and link libhcir_b200.so in-tree."""
     if not force and is_current():
         return LIB_PATH
-    nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    # One builder at a time: under torchrun every rank of a fresh checkout gets here at once.  The
+    # others wait on the lock, find the stamp current and return; the .so is linked to a temporary
+    # name and renamed into place, so nobody ever maps a half-written library.
+    import fcntl
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB_PATH
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir: str, verbose: bool) -> str:
+    nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
@@ -73,12 +88,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         for _, log in results:
             print(log)
     objs = [o for o, _ in results]
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs],
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(STAMP, "w") as f:
+    os.replace(tmp, LIB_PATH)
+    with open(STAMP + ".tmp", "w") as f:
         f.write(_digest())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB_PATH
 
 

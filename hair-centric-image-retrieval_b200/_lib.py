@@ -27,6 +27,17 @@ class Plan(C.Structure):
         return 3 if self.sample_rows > 0 else 1
 
 
+class Tail(C.Structure):
+    """hcir_tail_t: what every query's CTA of hcir_select_rescore does with its finished top-k
+    (label gather, vote, stores into the peer regions).  A zero-initialised Tail does nothing."""
+    _fields_ = [("labels", C.c_void_p), ("n_labels", C.c_int64), ("num_classes", C.c_int32), ("T", C.c_float),
+                ("classes", C.c_void_p), ("pred", C.c_void_p), ("out_lab", C.c_void_p),
+                ("world", C.c_int32), ("rank", C.c_int32), ("payload", C.c_int32), ("reserved_", C.c_int32),
+                ("slot_bytes", C.c_uint64), ("regions", C.c_void_p * 16), ("step", C.c_void_p)]
+
+
+PAYLOAD_BLOCK, PAYLOAD_PRED = 1, 2
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _INT = C.c_int
@@ -43,7 +54,7 @@ SIGNATURES = {
     "hcir_simtopk": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P]),
     "hcir_simtopk_debug": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P, _P]),
     "hcir_select_rescore": (_INT, [_P, _P, _INT, _I64, _I64, _INT, _I64, C.POINTER(Plan), _P, _P, _F, _F,
-                                   _P, _P, _P, _P, _P]),
+                                   _P, _P, _P, _P, C.POINTER(Tail), _P]),
     "hcir_exact_workspace_bytes": (C.c_size_t, [_I64, _I64, _INT, _INT]),
     "hcir_exact_topk": (_INT, [_P, _P, _INT, _I64, _INT, _I64, _P, _I64, _P, _P, _P, C.c_size_t, _INT, _P]),
     "hcir_gather_labels": (_INT, [_P, _I64, _P, _I64, _I64, _P, _P]),
@@ -61,8 +72,9 @@ SIGNATURES = {
     "hcir_peer_close": (_INT, [_P]),
     "hcir_peer_free": (_INT, [_P]),
     "hcir_peer_push": (_INT, [_P, C.c_size_t, C.POINTER(_P), _INT, _INT, C.c_size_t, _P, _P, _P]),
-    "hcir_peer_wait": (_INT, [_P, _INT, _P, _INT, _I64, _P]),
-    "hcir_merge_topk_peer": (_INT, [_P, _INT, _I64, _INT, _INT, C.c_size_t, _P, _P, _P, _P, _P]),
+    "hcir_peer_wait": (_INT, [_P, _INT, _P, _I64, _P]),
+    "hcir_peer_merge_vote": (_INT, [_P, _INT, _I64, _INT, _INT, C.c_size_t, _P, _I64, _P, _P, _P, _INT, _F, _P, _P,
+                                    _P]),
 }
 
 _lib = None
@@ -80,7 +92,7 @@ def load(build_if_missing: bool = True):
     path = library_path()
     if build_if_missing and not _build.is_current():
         try:
-            _build.build_library()
+            _build.build_library()   # serialised across processes by a file lock (torchrun: one rank builds)
         except Exception as e:  # no nvcc on this box: use the shipped .so if there is one
             if not os.path.exists(path):
                 raise RuntimeError(
@@ -93,7 +105,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here == ABI/header drift
         fn.restype = res
         fn.argtypes = args
-    if lib.hcir_abi_version() != 4:
+    if lib.hcir_abi_version() != 5:
         raise RuntimeError("hcir_b200: ABI version mismatch")
     _lib = lib
     return lib

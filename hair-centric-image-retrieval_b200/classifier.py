@@ -60,10 +60,9 @@ class KNeighborsClassifierB200:
         """(dist = clip(1 - cos, 0, 2) fp32 ascending, idx int64) like sklearn's cosine brute
         force (metrics/pairwise.py cosine_distances)."""
         self._check()
-        if X is None:
-            raise NotImplementedError("kneighbors(X=None) (leave-one-out on the training set) is not "
-                                      "on the reference's path")
         k = self.n_neighbors if n_neighbors is None else int(n_neighbors)
+        if X is None:
+            return self._kneighbors_of_training_set(k, return_distance)
         _, kind = _as_2d_f32(X, "X")
         sims, idx = self._bank.topk(X, k, mode=self.mode, return_device=True)
         if kind == "torch_cpu":
@@ -73,6 +72,28 @@ class KNeighborsClassifierB200:
             return idx_h
         dist = torch.clamp(1.0 - sims, 0.0, 2.0)
         return _to_host(dist, kind), idx_h
+
+    def _kneighbors_of_training_set(self, k: int, return_distance: bool):
+        """sklearn's ``kneighbors(X=None)``: the k nearest neighbours of every training row, the row
+        itself excluded (neighbors/_base.py: search k+1, drop the entry whose index is the row's own;
+        when a row has more than k duplicates and is not in its own list, drop the first entry)."""
+        bank = self._bank
+        if k + 1 > bank.n:
+            raise ValueError(f"Expected n_neighbors <= n_samples_fit - 1 = {bank.n - 1}, got {k}")
+        dists, inds = [], []
+        with torch.cuda.device(bank.device):
+            for a in range(0, bank.n, 1 << 15):
+                q = bank.g32[a: a + (1 << 15), : bank.d]          # unit rows: normalising again is a no-op up to rounding
+                sims, idx = bank.topk(q, k + 1, mode=self.mode, return_device=True)
+                own = torch.arange(a, a + q.shape[0], device=bank.device)[:, None]
+                keep = idx != own
+                keep[:, 0] &= ~keep.all(dim=1)                  # own row pushed out by duplicates: drop the first
+                inds.append(idx[keep].view(-1, k))
+                dists.append(torch.clamp(1.0 - sims[keep].view(-1, k), 0.0, 2.0))
+            ind = _to_host(torch.cat(inds), "numpy")
+            if not return_distance:
+                return ind
+            return _to_host(torch.cat(dists), "numpy"), ind
 
     def predict(self, X):
         self._check()

@@ -41,6 +41,16 @@ int check_device();  // HCIR_OK iff current device is sm_100
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// ---- peer region header (peer.cu; K3's tail and the fused wait+merge+vote kernel write / poll it) ----
+//   int64 words: [0..15] arrivals[r]  steps whose block from rank r has landed here (monotone)
+//                [16..31] meta[0][r], [32..47] meta[1][r]  one word per rank and parity (uncertified count)
+//                [48] step_seen  last completed step   [49] error  != 0: a wait timed out at that step
+//                [50] consumer done-CTA counter        [51] producer done-CTA counter (standalone push)
+constexpr int kPeerMax = 16;
+constexpr size_t kPeerHdrBytes = 512;
+constexpr int kPeerHdrArrivals = 0, kPeerHdrMeta = 16, kPeerHdrStep = 48, kPeerHdrError = 49;
+constexpr int kPeerHdrConsDone = 50, kPeerHdrProdDone = 51;
+
 __host__ __device__ inline int64_t ceil_div_i64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up_int(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -115,6 +125,68 @@ __device__ __forceinline__ void canonical_dot2(const float4* __restrict__ q4, co
   }
   sa = a;
   sb = b;
+}
+
+// ---- kNN vote by one warp ------------------------------------------------------------------
+// s[0..n) similarities in rank order, l[0..n) neighbour class indices (shared memory).  T <= 0:
+// uniform majority vote == sklearn `_mode`; T > 0: score[c] = sum exp((s_j - s_0) / T) accumulated in
+// rank order.  Lane l owns classes l, l+32, ...; arg-max, ties -> smallest class.  Every lane returns
+// the winning class index.  One definition for every kernel that votes (K4, K3's tail, K5's tail), so
+// their predictions are bit-identical.
+__device__ __forceinline__ int warp_vote(const float* s, const int32_t* l, int n, int num_classes, float T,
+                                         int lane) {
+  const bool weighted = T > 0.0f;
+  const float s0 = (weighted && n > 0) ? s[0] : 0.0f;
+  const float inv_t = weighted ? 1.0f / T : 0.0f;
+  float best = -1.0f;
+  int best_c = 0x7FFFFFFF;
+  for (int c = lane; c < num_classes; c += kWarp) {
+    float acc = 0.0f;
+    for (int j = 0; j < n; ++j) {
+      if (l[j] == c) acc += weighted ? expf((s[j] - s0) * inv_t) : 1.0f;
+    }
+    if (acc > best) {  // ascending c per lane: strict > keeps the smallest class on ties
+      best = acc;
+      best_c = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(kFull, best, o);
+    const int oc = __shfl_xor_sync(kFull, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) {
+      best = ob;
+      best_c = oc;
+    }
+  }
+  return best_c;
+}
+
+__device__ __forceinline__ int64_t ld_acquire_sys(const int64_t* p) {
+  int64_t v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Poll arrivals[lane] (lane < world) of a peer region header until every rank's block of step `st` has
+// landed, bounded by timeout_ns.  Called by one warp; returns true to every lane iff all arrived.
+__device__ __forceinline__ bool peer_wait_arrivals(const int64_t* hdr, int world, int64_t st, int64_t timeout_ns,
+                                                   int lane) {
+  bool ok = true;
+  if (lane < world) {
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(hdr + kPeerHdrArrivals + lane) < st) {
+      __nanosleep(32);
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (static_cast<int64_t>(t1 - t0) > timeout_ns) {  // a peer never arrived: report, do not hang the GPU
+        ok = false;
+        break;
+      }
+    }
+  }
+  return __all_sync(kFull, ok);
 }
 
 // ---- warp-cooperative exact selection ("prune") -----------------------------------------

@@ -3,88 +3,75 @@
 // Every rank owns one REGION of device memory (cudaMalloc, exported with CUDA IPC and mapped by
 // every other rank of the box), all regions laid out identically:
 //
-//   header (512 B, int64 words)   [0..15]  arrivals[r]   monotone count of "rank r's block landed"
+//   header (512 B, int64 words; hcir_common.cuh)
+//                                 [0..15]  arrivals[r]   steps whose block from rank r has landed here
 //                                 [16..31] meta[0][r]    one int64 per rank riding along with a block
 //                                 [32..47] meta[1][r]      (the sender's uncertified-query count)
-//                                 [48]     step_seen     step of the last completed wait
-//                                 [49]     error         != 0: a wait timed out
+//                                 [48]     step_seen     last completed step
+//                                 [49]     error         != 0: a wait timed out at that step
+//                                 [50/51]  done-CTA counters of the consumer / the standalone push
 //   data   2 parities x world slots x slot_stride bytes:  slot (p, r) = rank r's block of a step
 //                                 with (step & 1) == p
 //
-// push:  rank r stores its block into slot (step & 1, r) of EVERY region (its own included) with
-//        16-byte stores over NVLink, then -- per CTA: barrier, system-scope fence -- bumps
-//        arrivals[r] in every region.  No collective library call, no staging copy.
-// wait:  spins until arrivals[r] >= step * ctas_per_push for every r.
-// Two parities are enough: a rank can only be one step ahead of the slowest peer (its wait for
-// step n+1 needs that peer's push n+1, which that peer enqueues after its own reads of step n).
-// `step` lives in device memory and is incremented on the stream, so a captured CUDA graph
-// replays the exchange unchanged.
+// Protocol.  `step` (device int64, one per channel) counts COMPLETED steps.  The producer of step
+// st = *step + 1 stores rank r's block into slot (st & 1, r) of EVERY region (its own included) with
+// plain stores over NVLink; its last CTA -- every CTA fences at system scope and counts itself done --
+// writes the meta word and bumps arrivals[r] once in every region.  The producer is normally the TAIL
+// OF K3 (select_rescore.cu: every query's CTA stores its own results, no packed block is staged
+// locally); peer_push_kernel below is the standalone form for blocks that already sit in memory.
+// The consumer (peer_wait_kernel, or the fused wait+merge+vote kernel in merge.cu) spins until
+// arrivals[r] >= st for every r, reads the slots in place, and completes the step by writing
+// *step = st.  Two parities are enough: a rank can only be one step ahead of the slowest peer (its
+// wait for step n+1 needs that peer's block n+1, which that peer produces after it consumed step n).
+// Because `step` lives in device memory, a captured CUDA graph replays the exchange unchanged.
 #include <string.h>
 
 #include "hcir_common.cuh"
 
 namespace hcir {
 
-constexpr int kPeerMax = 16;
-constexpr int kHdrArrivals = 0, kHdrMeta = 16, kHdrStep = 48, kHdrError = 49;
-constexpr size_t kHdrBytes = 512;
 constexpr int kPushThreads = 256;
 
 struct PeerPtrs {
   char* region[kPeerMax];
 };
 
-__device__ __forceinline__ int64_t ld_acquire_sys(const int64_t* p) {
-  int64_t v;
-  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 __global__ void __launch_bounds__(kPushThreads)
 peer_push_kernel(const uint4* __restrict__ src, size_t n16, PeerPtrs peers, int world, int rank, size_t slot_stride,
                  const int64_t* __restrict__ step, const int32_t* __restrict__ meta_src) {
-  const int64_t st = *step;
+  const int64_t st = *step + 1;
   const size_t par = static_cast<size_t>(st & 1);
-  const size_t slot_off = kHdrBytes + (par * world + rank) * slot_stride;
+  const size_t slot_off = kPeerHdrBytes + (par * world + rank) * slot_stride;
   for (size_t i = static_cast<size_t>(blockIdx.x) * kPushThreads + threadIdx.x; i < n16;
        i += static_cast<size_t>(gridDim.x) * kPushThreads) {
     const uint4 v = src[i];
     for (int g = 0; g < world; ++g) reinterpret_cast<uint4*>(peers.region[g] + slot_off)[i] = v;
   }
-  if (blockIdx.x == 0 && threadIdx.x < world) {
-    const int64_t m = meta_src ? static_cast<int64_t>(*meta_src) : 0;
-    reinterpret_cast<int64_t*>(peers.region[threadIdx.x])[kHdrMeta + par * kPeerMax + rank] = m;
-  }
   __syncthreads();
-  if (threadIdx.x < world) {
-    __threadfence_system();  // this CTA's stores (observed through the barrier) before the arrival
-    atomicAdd_system(reinterpret_cast<unsigned long long*>(peers.region[threadIdx.x]) + kHdrArrivals + rank, 1ull);
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this CTA's stores (observed through the barrier) before it counts itself done
+    unsigned long long* done = reinterpret_cast<unsigned long long*>(peers.region[rank]) + kPeerHdrProdDone;
+    if (atomicAdd(done, 1ull) == gridDim.x - 1) {  // last CTA: everybody's stores are ordered before the arrival
+      __threadfence();
+      *done = 0ull;
+      const int64_t m = meta_src ? static_cast<int64_t>(*meta_src) : 0;
+      for (int g = 0; g < world; ++g)
+        reinterpret_cast<int64_t*>(peers.region[g])[kPeerHdrMeta + par * kPeerMax + rank] = m;
+      __threadfence_system();
+      for (int g = 0; g < world; ++g)
+        atomicAdd_system(reinterpret_cast<unsigned long long*>(peers.region[g]) + kPeerHdrArrivals + rank, 1ull);
+    }
   }
 }
 
 __global__ void __launch_bounds__(32)
-peer_wait_kernel(int64_t* __restrict__ hdr, int world, const int64_t* __restrict__ step, int64_t ctas_per_push,
-                 int64_t timeout_ns) {
-  const int64_t st = *step;
-  const int64_t target = st * ctas_per_push;
-  bool ok = true;
-  if (threadIdx.x < world) {
-    uint64_t t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(hdr + kHdrArrivals + threadIdx.x) < target) {
-      __nanosleep(64);
-      uint64_t t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (static_cast<int64_t>(t1 - t0) > timeout_ns) {  // a peer never arrived: report, do not hang the GPU
-        ok = false;
-        break;
-      }
-    }
-  }
-  const bool all_ok = __all_sync(kFull, ok);
+peer_wait_kernel(int64_t* __restrict__ hdr, int world, int64_t* __restrict__ step, int64_t timeout_ns) {
+  const int64_t st = *step + 1;
+  const bool all_ok = peer_wait_arrivals(hdr, world, st, timeout_ns, threadIdx.x);
   if (threadIdx.x == 0) {
-    hdr[kHdrStep] = st;
-    if (!all_ok) hdr[kHdrError] = st;
+    *step = st;
+    hdr[kPeerHdrStep] = st;
+    if (!all_ok) hdr[kPeerHdrError] = st;
   }
 }
 
@@ -93,12 +80,12 @@ peer_wait_kernel(int64_t* __restrict__ hdr, int world, const int64_t* __restrict
 extern "C" size_t hcir_peer_region_bytes(int world, size_t slot_bytes) {
   if (world < 1 || world > hcir::kPeerMax) return 0;
   const size_t stride = (slot_bytes + 255) / 256 * 256;
-  return hcir::kHdrBytes + 2 * static_cast<size_t>(world) * stride;
+  return hcir::kPeerHdrBytes + 2 * static_cast<size_t>(world) * stride;
 }
 
 extern "C" size_t hcir_peer_slot_offset(int world, size_t slot_bytes, int parity, int rank) {
   const size_t stride = (slot_bytes + 255) / 256 * 256;
-  return hcir::kHdrBytes + (static_cast<size_t>(parity & 1) * world + rank) * stride;
+  return hcir::kPeerHdrBytes + (static_cast<size_t>(parity & 1) * world + rank) * stride;
 }
 
 extern "C" int hcir_peer_push_ctas(size_t bytes) {
@@ -109,7 +96,7 @@ extern "C" int hcir_peer_push_ctas(size_t bytes) {
 
 extern "C" int hcir_peer_alloc(size_t bytes, void** ptr, void* ipc_handle_64) {
   using namespace hcir;
-  HCIR_REQUIRE(ptr != nullptr && ipc_handle_64 != nullptr && bytes >= kHdrBytes, "peer_alloc: bad arguments");
+  HCIR_REQUIRE(ptr != nullptr && ipc_handle_64 != nullptr && bytes >= kPeerHdrBytes, "peer_alloc: bad arguments");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
   void* p = nullptr;
   HCIR_CUDA_TRY(cudaMalloc(&p, bytes));
@@ -170,13 +157,13 @@ extern "C" int hcir_peer_push(const void* src, size_t bytes, void* const* region
   return HCIR_OK;
 }
 
-extern "C" int hcir_peer_wait(void* region_local, int world, const int64_t* step, int ctas_per_push,
-                              int64_t timeout_ns, hcir_stream_t stream) {
+extern "C" int hcir_peer_wait(void* region_local, int world, int64_t* step, int64_t timeout_ns,
+                              hcir_stream_t stream) {
   using namespace hcir;
-  HCIR_REQUIRE(region_local != nullptr && step != nullptr && world >= 1 && world <= kPeerMax && ctas_per_push >= 1,
+  HCIR_REQUIRE(region_local != nullptr && step != nullptr && world >= 1 && world <= kPeerMax,
                "peer_wait: bad arguments");
   peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<int64_t*>(region_local), world, step,
-                                                                    ctas_per_push, timeout_ns);
+                                                                    timeout_ns);
   HCIR_CUDA_TRY(cudaGetLastError());
   return HCIR_OK;
 }

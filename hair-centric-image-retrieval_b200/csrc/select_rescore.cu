@@ -1,18 +1,26 @@
-// K3: per-query candidate selection, adaptive fp32 re-score, exact sort, certification.
-// One CTA per query.  Bandwidth / latency-bound: ONE streaming read of the query's candidate
-// lists (the sample pass supplies a staging hint thr_hi[q] that ~4*kc candidates exceed, so
-// the kc best can be picked from a small shared-memory stage without a second pass; a
-// histogram-select fallback covers the cases where the hint is off) plus ~ (k + 16 +
-// near-boundary candidates) fp32 gallery rows of 4*ld bytes.
+// K3: per-query candidate selection, adaptive fp32 re-score, exact sort, certification -- and the
+// TAIL of the step fused behind it: neighbour-label gather, kNN vote, and the store of the query's
+// results straight into every rank's peer region over NVLink (multi-GPU), with one arrival signal per
+// rank and step.  One CTA per query.
+//
+// Bandwidth / latency-bound: ONE streaming read of the query's candidate lists (the sample pass
+// supplies a staging hint thr_hi[q] that ~4*kc candidates exceed, so the kc best can be picked from
+// a small shared-memory stage without a second pass; a histogram-select fallback covers the cases
+// where the hint is off) plus ~ (k + 6 + near-boundary candidates) fp32 gallery rows of 4*ld bytes.
+//
+// Measured shape of the round-1 kernel (ncu --set full, C2, profiles/): 29 % of the stall samples in
+// the list read + staging loop (one shared-memory atomic per staged key: short-scoreboard), 25 % in
+// the row gathers, 21 % at barriers.  Hence: (a) lists are walked as a queue of 32-key chunks so a
+// lane always has kKeyBatch independent loads in flight whatever the list lengths are, (b) staging
+// reserves room with ONE atomic per warp and batch (shuffle prefix over per-lane hit counts),
+// (c) few queries (the streaming regime) get 1024-thread CTAs: 32 warps share the list walk, one
+// fp32 row per warp in the re-score, one warp per key in the rank sort.
 #include <math.h>
 
 #include "hcir_common.cuh"
 
 namespace hcir {
 
-// CTA width is a template parameter: 256 threads x 5 CTAs/SM in general, 128 threads x 10 CTAs/SM for
-// small k and many queries (measured on C2, k=20: 0.45 -> 0.40 ms -- twice as many queries in flight hide
-// the barrier / gather latencies -- while k=100/200 and the 64-query streaming regime lose 40-60 %).
 constexpr int kRound1Slack = 6;
 constexpr int kBins = 2048;  // histogram bins of the fallback streaming selection
 
@@ -37,53 +45,129 @@ static SelSmem sel_smem_layout(int nlists, int kc, int ld) {
   return L;
 }
 
-// Visit every candidate key of this query: warp w walks lists w, w+8, ...; lanes stride over a
-// list (coalesced 256-byte reads), kKeyBatch loads in flight per lane before any is consumed
-// (the visitor has shared-memory side effects the compiler will not hoist loads across).
+// device-side form of hcir_tail_t
+struct TailParams {
+  const int32_t* labels;
+  int64_t n_labels;
+  int num_classes;
+  float T;
+  const int64_t* classes;
+  int64_t* pred;
+  int32_t* out_lab;
+  int world, rank, payload;
+  size_t slot_stride;
+  char* region[kPeerMax];
+  const int64_t* step;
+};
+
+// Visit every candidate key of this query in batches: the lists of warp w (w, w+W, ...) form a queue
+// of 32-key chunks; every round takes the next kKeyBatch chunks, issues all their loads, then hands
+// the batch to the visitor (kk[u] == 0: no key; RAW keys, their index part is never 0).
 constexpr int kKeyBatch = 8;
 template <int kSelThreads, typename F>
-__device__ __forceinline__ void for_each_key(const uint64_t* __restrict__ lists, const int32_t* cnts, int nlists,
-                                             int cap, int warp, int lane, F&& f) {
+__device__ __forceinline__ void for_each_batch(const uint64_t* __restrict__ lists, const int32_t* cnts, int nlists,
+                                               int cap, int warp, int lane, F&& f) {
   constexpr int kSelWarps = kSelThreads / kWarp;
-  for (int s = warp; s < nlists; s += kSelWarps) {
-    const int c = cnts[s];
-    const uint64_t* src = lists + static_cast<int64_t>(s) * cap;
-    for (int base = 0; base < c; base += kWarp * kKeyBatch) {
-      uint64_t kk[kKeyBatch];
+  int s = warp, base = 0;
+  int c = (s < nlists) ? cnts[s] : 0;
+  for (;;) {
+    uint64_t kk[kKeyBatch];
+    bool any = false;
 #pragma unroll
-      for (int u = 0; u < kKeyBatch; ++u) {
-        const int i = base + u * kWarp + lane;
-        kk[u] = (i < c) ? __ldcg(src + i) : 0ull;  // lists hold RAW keys; index part is never 0
+    for (int u = 0; u < kKeyBatch; ++u) {
+      while (s < nlists && base >= c) {  // warp-uniform: next non-empty list of this warp
+        s += kSelWarps;
+        base = 0;
+        c = (s < nlists) ? cnts[s] : 0;
       }
+      kk[u] = 0ull;
+      if (s < nlists) {
+        const int i = base + lane;
+        if (i < c) kk[u] = __ldcg(lists + static_cast<int64_t>(s) * cap + i);
+        base += kWarp;
+        any = true;
+      }
+    }
+    if (!any) break;
+    f(kk);
+  }
+}
+
+// Append the keys of a batch whose ordered score exceeds (or reaches) `lim` to stage[]: every lane
+// counts its hits, a shuffle prefix gives its offset, ONE shared-memory atomic per warp reserves
+// the room.  Keys beyond stage_cap are dropped (the caller sees the count).
+template <bool kInclusive>
+__device__ __forceinline__ void stage_batch(const uint64_t (&kk)[kKeyBatch], uint32_t lim, uint64_t* stage,
+                                            int stage_cap, uint32_t* counter, int lane) {
+  uint32_t hits = 0u;
 #pragma unroll
-      for (int u = 0; u < kKeyBatch; ++u)
-        if (kk[u] != 0ull) f(raw2key(kk[u]));
+  for (int u = 0; u < kKeyBatch; ++u) {
+    if (kk[u] != 0ull) {
+      const uint32_t o = f2ord(__uint_as_float(static_cast<uint32_t>(kk[u] >> 32)));
+      if (kInclusive ? (o >= lim) : (o > lim)) hits |= 1u << u;
+    }
+  }
+  const int n = __popc(hits);
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < kWarp; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(kFull, incl, kWarp - 1);
+  if (total == 0) return;  // warp-uniform
+  uint32_t base = 0u;
+  if (lane == kWarp - 1) base = atomicAdd(counter, static_cast<uint32_t>(total));
+  base = __shfl_sync(kFull, base, kWarp - 1);
+  uint32_t at = base + static_cast<uint32_t>(incl - n);
+#pragma unroll
+  for (int u = 0; u < kKeyBatch; ++u) {
+    if (hits & (1u << u)) {
+      if (at < static_cast<uint32_t>(stage_cap)) stage[at] = raw2key(kk[u]);
+      ++at;
     }
   }
 }
 
 // rank (number of strictly greater keys) of every key[0..n) -> dst[rank] = key for rank < keep.
-// Keys are unique, so ranks are a permutation.  The caller syncs.
-template <int kSelThreads>
+// Keys are unique, so ranks are a permutation.  The caller syncs.  kWarpPerKey: one warp per key,
+// lanes split the scan (wide CTAs, short arrays), else one thread per key.
+template <int kSelThreads, bool kWarpPerKey>
 __device__ __forceinline__ void rank_scatter(const uint64_t* keys, int n, uint64_t* dst, int keep, int tid) {
-  for (int j = tid; j < n; j += kSelThreads) {
-    const uint64_t mine = keys[j];
-    int rank = 0;
-    for (int i = 0; i < n; ++i) rank += (keys[i] > mine) ? 1 : 0;
-    if (rank < keep) dst[rank] = mine;
+  if constexpr (kWarpPerKey) {
+    const int lane = tid & 31;
+    for (int j = tid >> 5; j < n; j += kSelThreads / kWarp) {
+      const uint64_t mine = keys[j];
+      int rank = 0;
+      for (int i = lane; i < n; i += kWarp) rank += (keys[i] > mine) ? 1 : 0;
+      rank = __reduce_add_sync(kFull, rank);
+      if (lane == 0 && rank < keep) dst[rank] = mine;
+    }
+  } else {
+    for (int j = tid; j < n; j += kSelThreads) {
+      const uint64_t mine = keys[j];
+      int rank = 0;
+      for (int i = 0; i < n; ++i) rank += (keys[i] > mine) ? 1 : 0;
+      if (rank < keep) dst[rank] = mine;
+    }
   }
 }
 
+// kSelThreads: 128 threads x 10 CTAs/SM (k <= 32, many queries: twice as many queries in flight hide the
+// barrier / gather latencies), 256 x 5 in general, 1024 for few queries (streaming regime: the per-query
+// latency IS the kernel time, so the whole CTA width goes to one query).
 template <int kSelThreads>
-__global__ void __launch_bounds__(kSelThreads, 1280 / kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, (kSelThreads >= 1024) ? 1 : 1280 / kSelThreads)
 select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int ld, int64_t nq,
                       int64_t ng, int k, int64_t idx_offset, int nlists, int cap, int kc,
                       const int32_t* __restrict__ counts, const uint64_t* __restrict__ cand,
                       const float* __restrict__ thr_out, const float* __restrict__ thr_hi,
                       const float* __restrict__ q_delta, float g_delta_max, float eps_acc,
                       float* __restrict__ out_sim, int64_t* __restrict__ out_idx,
-                      int32_t* __restrict__ uncert_list, int32_t* __restrict__ uncert_count, SelSmem L) {
+                      int32_t* __restrict__ uncert_list, int32_t* __restrict__ state, SelSmem L,
+                      const TailParams tail) {
   constexpr int kSelWarps = kSelThreads / kWarp;
+  constexpr bool kWide = (kSelThreads >= 1024);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw + L.stage);
   uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw + L.sel);   // kc best by bf16 score, DESCENDING
@@ -99,7 +183,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   const uint64_t* lists = cand + q * nlists * static_cast<int64_t>(cap);
 
   // ---- start: issue the query-row loads (consumed after the key pass); every warp fetches the
-  // lengths / thresholds of ITS lists (w, w+8, ...) and goes straight to reading keys -- there is
+  // lengths / thresholds of ITS lists (w, w+W, ...) and goes straight to reading keys -- there is
   // no serial prefix phase; totals are combined with shared-memory atomics -----------------------
   constexpr int kQv = 2;  // float4 per thread held in registers: covers ld <= 2048 (the rest is loaded late)
   float4 qv[kQv];
@@ -116,6 +200,9 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     scratch[6] = 0;
     scratch[7] = 0;
     scratch[9] = 0;             // staged count
+    scratch[10] = 0;            // fallback bin scan result: bin 0 / nothing above / nothing in it = "take every
+    scratch[11] = 0;            //   key in range" -- what remains in force when fewer than kc keys exist and no
+    scratch[12] = 0;            //   bin reaches the kc-th rank
     scratch[13] = 0;            // keys outside the assumed score range
     scratch[14] = 0xFFFFFFFFu;  // smallest list threshold (ordered bits)
     scratch[18] = 0;            // total candidates
@@ -154,11 +241,8 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   int nstage = 0;
   bool staged = false;
   {
-    for_each_key<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
-      if (static_cast<uint32_t>(key >> 32) > hint) {
-        const uint32_t at = atomicAdd(&scratch[9], 1u);
-        if (at < static_cast<uint32_t>(L.stage_cap)) stage[at] = key;
-      }
+    for_each_batch<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](const uint64_t (&kk)[kKeyBatch]) {
+      stage_batch<false>(kk, hint, stage, L.stage_cap, &scratch[9], lane);
     });
     // the query row goes to shared memory now that the key loads have been issued
 #pragma unroll
@@ -198,10 +282,14 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       while ((span >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
       for (int b = tid; b < kBins; b += kSelThreads) hist[b] = 0;
       __syncthreads();
-      for_each_key<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
-        const uint32_t o = static_cast<uint32_t>(key >> 32);
-        if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
-        else if (check_range) scratch[13] = 1u;
+      for_each_batch<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](const uint64_t (&kk)[kKeyBatch]) {
+#pragma unroll
+        for (int u = 0; u < kKeyBatch; ++u) {
+          if (kk[u] == 0ull) continue;
+          const uint32_t o = f2ord(__uint_as_float(static_cast<uint32_t>(kk[u] >> 32)));
+          if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
+          else if (check_range) scratch[13] = 1u;
+        }
       });
       __syncthreads();
       if (check_range) {
@@ -250,11 +338,8 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     }
     // collect everything at or above the cut (exact ties beyond the staging room are dropped:
     // they score == the kc-th best, which the certification bound below covers)
-    for_each_key<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](uint64_t key) {
-      if (static_cast<uint32_t>(key >> 32) >= cut) {
-        const uint32_t at = atomicAdd(&scratch[9], 1u);
-        if (at < static_cast<uint32_t>(L.stage_cap)) stage[at] = key;
-      }
+    for_each_batch<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](const uint64_t (&kk)[kKeyBatch]) {
+      stage_batch<true>(kk, cut, stage, L.stage_cap, &scratch[9], lane);
     });
     __syncthreads();
     nstage = min(static_cast<int>(scratch[9]), L.stage_cap);
@@ -322,25 +407,47 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     const int keep = static_cast<int>(scratch[11]);
     __syncthreads();  // everyone has read the scan result: the histogram memory may be reused
     if (keep <= kCompactCap) {
-      for (int i = tid; i < nstage; i += kSelThreads) {
-        const uint64_t key = stage[i];
-        if (static_cast<uint32_t>(key >> 32) >= cut) compact[atomicAdd(&scratch[17], 1u)] = key;
+      // one atomic per warp and round of 32 keys (ballot prefix), not one per kept key
+      for (int i0 = warp * kWarp; i0 < nstage; i0 += kSelThreads) {
+        const int i = i0 + lane;
+        const uint64_t key = (i < nstage) ? stage[i] : 0ull;
+        const bool hit = (i < nstage) && (static_cast<uint32_t>(key >> 32) >= cut);
+        const uint32_t b = __ballot_sync(kFull, hit);
+        if (b == 0u) continue;
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(&scratch[17], static_cast<uint32_t>(__popc(b)));
+        base = __shfl_sync(kFull, base, 0);
+        if (hit) compact[base + __popc(b & ((1u << lane) - 1u))] = key;
       }
       __syncthreads();
       pool = compact;
       npool = keep;
     }
   }
-  rank_scatter<kSelThreads>(pool, npool, sel, kc, tid);
+  rank_scatter<kSelThreads, kWide>(pool, npool, sel, kc, tid);
   __syncthreads();
-  if (nstage > kc) tprime = fmaxf(tprime, key_sim(sel[kc - 1]));
+  // Listed keys that did not make it into `sel` are bounded by sel's worst score -- whether they were
+  // staged and lost the kc cut (nstage > kc) or never staged at all (nstage == kc exactly: they sit at
+  // or below the staging hint / the fallback cut, which every staged key exceeds).  Only when every
+  // listed key is in `sel` (total <= kc) do the list thresholds alone bound the excluded rows.
+  if (nstage >= kc && total > kc) tprime = fmaxf(tprime, key_sim(sel[kc - 1]));
 
   const float dq = q_delta ? q_delta[q] : 0.0f;
   const float eps = g_delta_max * (1.0f + dq) + dq * (1.0f + 1e-6f) + eps_acc;
 
-  // fp32 re-score of sel[a..b): two rows per warp step
+  // fp32 re-score of sel[a..b): one row per warp while the warps suffice, else two rows per warp step
   auto rescore = [&](int a, int b) {
     const float4* q4 = reinterpret_cast<const float4*>(qrow);
+    if (b - a <= kSelWarps) {
+      const int j = a + warp;
+      if (j < b) {
+        const uint32_t r0 = key_idx(sel[j]);
+        const float s0 =
+            canonical_dot(q4, reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(r0) * ld), ld4, lane);
+        if (lane == 0) fk[j] = make_key(s0, r0);
+      }
+      return;
+    }
     for (int j = a + 2 * warp; j < b; j += 2 * kSelWarps) {
       const uint32_t r0 = key_idx(sel[j]);
       const bool two = (j + 1 < b);
@@ -380,12 +487,15 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   __syncthreads();
 
   // ---- exact order of the re-scored set, emit top-k ---------------------------------------
+  // (sel is dead from here on: its memory receives the final keys in rank order for the tail)
+  uint64_t* res = sel;
   for (int t = tid; t < nr; t += kSelThreads) {
     const uint64_t mine = fk[t];
     int rank = 0;
     for (int i = 0; i < nr; ++i) rank += (fk[i] > mine) ? 1 : 0;
     if (rank < k) {
       const float s = key_sim(mine);
+      res[rank] = mine;
       out_sim[q * k + rank] = s;
       out_idx[q * k + rank] = static_cast<int64_t>(key_idx(mine)) + idx_offset;
       if (rank == k - 1) scratch[7] = __float_as_uint(s);
@@ -396,8 +506,156 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     const float sk = (nr >= k) ? __uint_as_float(scratch[7]) : -INFINITY;
     // rows outside `sel` score <= tprime in bf16 (list thresholds, kc cut), hence <= tprime + eps in fp32
     const bool certified = (nr >= k) && (tprime + eps < sk);
-    if (!certified) uncert_list[atomicAdd(uncert_count, 1)] = static_cast<int32_t>(q);
+    if (!certified) uncert_list[atomicAdd(&state[0], 1)] = static_cast<int32_t>(q);
   }
+
+  // ======================= tail: labels -> vote -> peers -> arrival =======================
+  const int nres = nr < k ? nr : k;  // (< k only for uncertified queries, which are completed later)
+  // the stage is dead since the rank sort: it holds the neighbour class indices and similarities in rank order
+  int32_t* lab = reinterpret_cast<int32_t*>(stage);    // [k]
+  float* rsim = reinterpret_cast<float*>(stage) + k;  // [k]   (k <= kc <= stage_cap / 8)
+  if (tail.labels != nullptr) {
+    for (int j = tid; j < k; j += kSelThreads) {
+      int32_t l = -1;
+      float s = -INFINITY;
+      if (j < nres) {
+        const int64_t r = static_cast<int64_t>(key_idx(res[j]));
+        l = (r < tail.n_labels) ? __ldg(tail.labels + r) : -1;
+        s = key_sim(res[j]);
+      }
+      lab[j] = l;
+      rsim[j] = s;
+      if (tail.out_lab) tail.out_lab[q * k + j] = l;
+    }
+    __syncthreads();
+  }
+  int64_t pred_val = 0;
+  const bool do_vote = (tail.pred != nullptr) || (tail.payload == 2);
+  if (do_vote && warp == 0) {
+    const int best_c = warp_vote(rsim, lab, nres, tail.num_classes, tail.T, lane);
+    pred_val = tail.classes ? tail.classes[best_c] : static_cast<int64_t>(best_c);
+    if (lane == 0 && tail.pred) tail.pred[q] = pred_val;
+  }
+  if (tail.world > 0) {
+    // this query's results go straight into slot (parity of this step, rank) of EVERY rank's region
+    const int64_t st = *tail.step + 1;
+    const size_t slot_off = kPeerHdrBytes + (static_cast<size_t>(st & 1) * tail.world + tail.rank) * tail.slot_stride;
+    if (tail.payload == 1) {
+      const size_t e = static_cast<size_t>(nq) * k;
+      for (int i = tid; i < k * tail.world; i += kSelThreads) {
+        const int g = i / k, j = i - g * k;
+        char* base = tail.region[g] + slot_off;
+        const size_t at = static_cast<size_t>(q) * k + j;
+        const uint64_t key = (j < nres) ? res[j] : 0ull;
+        reinterpret_cast<int64_t*>(base)[at] = (j < nres) ? static_cast<int64_t>(key_idx(key)) + idx_offset : -1;
+        reinterpret_cast<float*>(base + e * 8)[at] = (j < nres) ? key_sim(key) : -INFINITY;
+        if (tail.labels) reinterpret_cast<int32_t*>(base + e * 12)[at] = lab[j];
+      }
+    } else if (tail.payload == 2) {
+      if (warp == 0 && lane < tail.world) reinterpret_cast<int64_t*>(tail.region[lane] + slot_off)[q] = pred_val;
+    }
+  }
+  // ---- last CTA of the launch: publish the uncertified count, reset the counters, signal the peers ----
+  __syncthreads();
+  if (tid == 0) {
+    if (tail.world > 0) __threadfence_system(); else __threadfence();
+    const int done = atomicAdd(&state[2], 1);
+    if (done == static_cast<int>(nq) - 1) {
+      __threadfence();
+      const int n_unc = atomicExch(&state[0], 0);
+      state[1] = n_unc;
+      state[2] = 0;
+      if (tail.world > 0) {
+        const int64_t st = *tail.step + 1;
+        const size_t par = static_cast<size_t>(st & 1);
+        for (int g = 0; g < tail.world; ++g)
+          reinterpret_cast<int64_t*>(tail.region[g])[kPeerHdrMeta + par * kPeerMax + tail.rank] = n_unc;
+        // every CTA's block stores (ordered before its done-count) and the metas, then the arrival
+        __threadfence_system();
+        for (int g = 0; g < tail.world; ++g)
+          atomicAdd_system(reinterpret_cast<unsigned long long*>(tail.region[g]) + kPeerHdrArrivals + tail.rank, 1ull);
+      }
+    }
+  }
+}
+
+static int launch_select(const float* q_f32, const float* g_f32, int ld, int64_t nq, int64_t ng, int k,
+                         int64_t idx_offset, const hcir_plan_t* plan, const void* workspace, const float* q_delta,
+                         float g_delta_max, float eps_acc, float* out_sim, int64_t* out_idx, int32_t* uncert_list,
+                         int32_t* state, const hcir_tail_t* tail, hcir_stream_t stream) {
+  HCIR_REQUIRE(plan != nullptr, "select_rescore: null plan");
+  HCIR_REQUIRE(ld > 0 && ld % 64 == 0, "select_rescore: ld=%d must be a positive multiple of 64", ld);
+  HCIR_REQUIRE(nq >= 0 && ng > 0, "select_rescore: bad shape");
+  HCIR_REQUIRE(k > 0 && k <= ng && k <= plan->kc, "select_rescore: need 1 <= k=%d <= min(ng=%lld, kc=%d)", k,
+               (long long)ng, plan->kc);
+  HCIR_REQUIRE(q_f32 && g_f32 && workspace && out_sim && out_idx && uncert_list && state,
+               "select_rescore: null pointer");
+  TailParams tp{};
+  if (tail != nullptr) {
+    HCIR_REQUIRE(tail->world >= 0 && tail->world <= kPeerMax && tail->rank >= 0 &&
+                     (tail->world == 0 || tail->rank < tail->world),
+                 "select_rescore: bad tail rank %d / world %d", tail->rank, tail->world);
+    HCIR_REQUIRE(tail->payload >= 0 && tail->payload <= 2, "select_rescore: bad tail payload %d", tail->payload);
+    const bool votes = tail->pred != nullptr || (tail->world > 0 && tail->payload == 2);
+    HCIR_REQUIRE(!votes || (tail->labels != nullptr && tail->num_classes > 0),
+                 "select_rescore: a vote needs labels and num_classes");
+    HCIR_REQUIRE(tail->world == 0 || (tail->step != nullptr && tail->payload != 0),
+                 "select_rescore: a peer tail needs a step counter and a payload");
+    HCIR_REQUIRE(tail->out_lab == nullptr || tail->labels != nullptr, "select_rescore: out_lab without labels");
+    tp.labels = tail->labels;
+    tp.n_labels = tail->n_labels;
+    tp.num_classes = tail->num_classes;
+    tp.T = tail->T;
+    tp.classes = tail->classes;
+    tp.pred = tail->pred;
+    tp.out_lab = tail->out_lab;
+    tp.world = tail->world;
+    tp.rank = tail->rank;
+    tp.payload = tail->world > 0 ? tail->payload : 0;
+    tp.slot_stride = (tail->slot_bytes + 255) / 256 * 256;
+    tp.step = tail->step;
+    if (tail->world > 0) {
+      const size_t need = tail->payload == 1 ? hcir_packed_block_bytes(nq, k, tail->labels != nullptr ? 1 : 0)
+                                             : static_cast<size_t>(nq) * 8;
+      HCIR_REQUIRE(need <= tail->slot_bytes, "select_rescore: peer slot of %zu bytes is smaller than the %zu-byte block",
+                   static_cast<size_t>(tail->slot_bytes), need);
+      for (int g = 0; g < tail->world; ++g) {
+        HCIR_REQUIRE(tail->regions[g] != nullptr, "select_rescore: peer region %d is null", g);
+        tp.region[g] = static_cast<char*>(tail->regions[g]);
+      }
+    }
+  }
+  int rc = check_device();
+  if (rc != HCIR_OK) return rc;
+  if (nq == 0) return HCIR_OK;
+  const SelSmem L = sel_smem_layout(plan->nlists, plan->kc, ld);
+  HCIR_REQUIRE(L.total <= 220 * 1024, "select_rescore: kc=%d ld=%d needs %zu B of shared memory", plan->kc, ld,
+               L.total);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* ws = static_cast<const char*>(workspace);
+  const int32_t* counts = reinterpret_cast<const int32_t*>(ws + plan->counts_off);
+  const uint64_t* cand = reinterpret_cast<const uint64_t*>(ws + plan->keys_off);
+  const float* thr_out = reinterpret_cast<const float*>(ws + plan->thr_out_off);
+  const float* thr_hi = plan->sample_rows > 0 ? reinterpret_cast<const float*>(ws + plan->thr_hi_off) : nullptr;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define HCIR_LAUNCH_SEL(T_)                                                                                        \
+  do {                                                                                                             \
+    HCIR_CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                       static_cast<int>(L.total)));                                                \
+    select_rescore_kernel<T_><<<static_cast<unsigned>(nq), T_, L.total, st>>>(                                     \
+        q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi, \
+        q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, state, L, tp);                               \
+  } while (0)
+  // CTA width: forced by the plan flags (measurement aid) or chosen from the shape
+  const int width = (plan->flags & HCIR_FLAG_K3_WIDTH_MASK) >> HCIR_FLAG_K3_WIDTH_SHIFT;
+  if (width == 3 || (width == 0 && nq <= 2 * static_cast<int64_t>(sms))) HCIR_LAUNCH_SEL(1024);
+  else if (width == 1 || (width == 0 && k <= 32 && nq >= 2048)) HCIR_LAUNCH_SEL(128);
+  else HCIR_LAUNCH_SEL(256);
+#undef HCIR_LAUNCH_SEL
+  HCIR_CUDA_TRY(cudaGetLastError());
+  return HCIR_OK;
 }
 
 }  // namespace hcir
@@ -405,38 +663,8 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
 extern "C" int hcir_select_rescore(const float* q_f32, const float* g_f32, int ld, int64_t nq, int64_t ng, int k,
                                    int64_t idx_offset, const hcir_plan_t* plan, const void* workspace,
                                    const float* q_delta, float g_delta_max, float eps_acc, float* out_sim,
-                                   int64_t* out_idx, int32_t* uncert_list, int32_t* uncert_count,
-                                   hcir_stream_t stream) {
-  using namespace hcir;
-  HCIR_REQUIRE(plan != nullptr, "select_rescore: null plan");
-  HCIR_REQUIRE(ld > 0 && ld % 64 == 0, "select_rescore: ld=%d must be a positive multiple of 64", ld);
-  HCIR_REQUIRE(nq >= 0 && ng > 0, "select_rescore: bad shape");
-  HCIR_REQUIRE(k > 0 && k <= ng && k <= plan->kc, "select_rescore: need 1 <= k=%d <= min(ng=%lld, kc=%d)", k,
-               (long long)ng, plan->kc);
-  HCIR_REQUIRE(q_f32 && g_f32 && workspace && out_sim && out_idx && uncert_list && uncert_count,
-               "select_rescore: null pointer");
-  int rc = check_device();
-  if (rc != HCIR_OK) return rc;
-  if (nq == 0) return HCIR_OK;
-  const SelSmem L = sel_smem_layout(plan->nlists, plan->kc, ld);
-  HCIR_REQUIRE(L.total <= 220 * 1024, "select_rescore: kc=%d ld=%d needs %zu B of shared memory", plan->kc, ld,
-               L.total);
-  const bool narrow = (k <= 32 && nq >= 2048);
-  HCIR_CUDA_TRY(cudaFuncSetAttribute(narrow ? select_rescore_kernel<128> : select_rescore_kernel<256>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)));
-  const char* ws = static_cast<const char*>(workspace);
-  const int32_t* counts = reinterpret_cast<const int32_t*>(ws + plan->counts_off);
-  const uint64_t* cand = reinterpret_cast<const uint64_t*>(ws + plan->keys_off);
-  const float* thr_out = reinterpret_cast<const float*>(ws + plan->thr_out_off);
-  const float* thr_hi = plan->sample_rows > 0 ? reinterpret_cast<const float*>(ws + plan->thr_hi_off) : nullptr;
-  if (narrow)
-    select_rescore_kernel<128><<<static_cast<unsigned>(nq), 128, L.total, static_cast<cudaStream_t>(stream)>>>(
-        q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi,
-        q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
-  else
-    select_rescore_kernel<256><<<static_cast<unsigned>(nq), 256, L.total, static_cast<cudaStream_t>(stream)>>>(
-        q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi,
-        q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, uncert_count, L);
-  HCIR_CUDA_TRY(cudaGetLastError());
-  return HCIR_OK;
+                                   int64_t* out_idx, int32_t* uncert_list, int32_t* uncert_state,
+                                   const hcir_tail_t* tail, hcir_stream_t stream) {
+  return hcir::launch_select(q_f32, g_f32, ld, nq, ng, k, idx_offset, plan, workspace, q_delta, g_delta_max, eps_acc,
+                             out_sim, out_idx, uncert_list, uncert_state, tail, stream);
 }

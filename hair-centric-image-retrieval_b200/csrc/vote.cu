@@ -79,31 +79,7 @@ vote_idx_kernel(const float* __restrict__ sims, const int64_t* __restrict__ idx,
     if (nbr_out) nbr_out[q * k + j] = lab;
   }
   __syncwarp();
-  const float* s = sims + q * k;
-  const bool weighted = T > 0.0f;
-  const float s0 = weighted ? s[0] : 0.0f;
-  const float inv_t = weighted ? 1.0f / T : 0.0f;
-  float best = -1.0f;
-  int best_c = 0x7FFFFFFF;
-  for (int c = lane; c < num_classes; c += kWarp) {
-    float acc = 0.0f;
-    for (int j = 0; j < k; ++j) {
-      if (l[j] == c) acc += weighted ? expf((s[j] - s0) * inv_t) : 1.0f;
-    }
-    if (acc > best) {
-      best = acc;
-      best_c = c;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(kFull, best, o);
-    const int oc = __shfl_xor_sync(kFull, best_c, o);
-    if (ob > best || (ob == best && oc < best_c)) {
-      best = ob;
-      best_c = oc;
-    }
-  }
+  const int best_c = warp_vote(sims + q * k, l, k, num_classes, T, lane);
   if (lane == 0) pred[q] = classes ? classes[best_c] : static_cast<int64_t>(best_c);
 }
 

@@ -11,11 +11,13 @@ Reference call sites this replaces (all CPU library calls in the reference):
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Plan
+from ._lib import Plan, Tail
 
 _SM_COUNT_CACHE: dict[int, int] = {}
 
@@ -154,6 +156,7 @@ class GalleryBank:
         # bench.py sets this to a list to get (name, start_event, end_event) per kernel launch
         self.kernel_events = None
         self.launches = 0  # number of hcir kernels launched by this bank since construction
+        self.k3_width = 0  # measurement aid: force K3's CTA width (1 = 128, 2 = 256, 3 = 1024 threads; 0 = auto)
 
     def _timed(self, name, fn, n_kernels=1):
         """Run one C-ABI launch; optionally bracket it with CUDA events on the current stream."""
@@ -177,6 +180,9 @@ class GalleryBank:
         cls_idx = np.searchsorted(self.classes_, y)
         if (cls_idx >= len(self.classes_)).any() or (self.classes_[np.minimum(cls_idx, len(self.classes_) - 1)] != y).any():
             raise ValueError("labels contain values missing from `classes`")
+        # captured graphs hold raw pointers to the old label / class tensors: drop them (collective
+        # if multi-GPU sessions exist -- sharded callers change labels on every rank together)
+        self.drop_sessions()
         self.labels = torch.from_numpy(cls_idx.astype(np.int32)).to(self.device)
         self._cls_dev = None
 
@@ -193,9 +199,11 @@ class GalleryBank:
         return self.tensor_path_for(self.n, k)
 
     # ------------------------------------------------------------------ search
-    def topk(self, queries, k: int, *, mode: str = "auto", return_device: bool = False):
+    def topk(self, queries, k: int, *, mode: str = "auto", return_device: bool = False, use_graph: bool = False):
         """Exact cosine top-k: (sims [Q,k] fp32 descending, idx [Q,k] int64), canonical order
-        (ties -> ascending index).  ``mode``: "auto" | "tensor" | "exact"."""
+        (ties -> ascending index).  ``mode``: "auto" | "tensor" | "exact".  ``use_graph``: serve the
+        batch from a cached fixed-shape :class:`SearchSession` (one CUDA-graph launch per call; worth it
+        for a caller that repeats the batch shape -- the session owns a workspace)."""
         q, kind = _as_2d_f32(queries, "queries")
         if q.shape[1] != self.d:
             raise ValueError(f"query dim {q.shape[1]} != gallery dim {self.d}")
@@ -207,7 +215,11 @@ class GalleryBank:
                 q = q.contiguous().to(self.device, non_blocking=True)
             elif q.device != self.device:
                 q = q.to(self.device)
-            sims, idx = self._topk_device(q, k, mode)
+            sess = self.session(q.shape[0], k, vote=False) if (use_graph and mode == "auto") else None
+            if sess is not None:
+                _, sims, idx = sess.run(q)
+            else:
+                sims, idx = self._topk_device(q, k, mode)
             if return_device or kind == "torch_cuda":
                 return sims, idx
             return _to_host(sims, kind), _to_host(idx, kind)
@@ -256,13 +268,14 @@ class GalleryBank:
                 qbf.data_ptr(), nq, self.gbf.data_ptr(), self.n, self.ld, plan, ws.data_ptr(), st),
                 n_kernels=plan.kernels()), "simtopk")
         unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
-        unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        unc_state = torch.zeros((4,), dtype=torch.int32, device=dev)   # [1] = result (include/hcir_b200.h)
+        plan.flags = self.k3_width << 8
         _lib.check(self._timed("select_rescore", lambda: lib.hcir_select_rescore(
             q32.data_ptr(), self.g32.data_ptr(), self.ld, nq, self.n, k, self.idx_offset, plan, ws.data_ptr(),
             qdl.data_ptr(), self.g_delta_max, self.eps_acc, out_sim.data_ptr(), out_idx.data_ptr(),
-            unc_list.data_ptr(), unc_cnt.data_ptr(), st)), "select_rescore")
+            unc_list.data_ptr(), unc_state.data_ptr(), None, st)), "select_rescore")
         res = tail(out_sim, out_idx) if tail else None
-        n_unc = int(unc_cnt.item())  # 4-byte readback: decides whether the exact fallback runs
+        n_unc = int(unc_state[1].item())  # 4-byte readback: decides whether the exact fallback runs
         if n_unc > 0:
             self._finish_uncertified(q32, qbf, qdl, unc_list, n_unc, k, out_sim, out_idx)
             res = tail(out_sim, out_idx) if tail else None
@@ -313,12 +326,12 @@ class GalleryBank:
         o_s = torch.empty((n_unc, k), dtype=torch.float32, device=dev)
         o_i = torch.empty((n_unc, k), dtype=torch.int64, device=dev)
         unc2 = torch.empty((n_unc,), dtype=torch.int32, device=dev)
-        cnt2 = torch.zeros((1,), dtype=torch.int32, device=dev)
+        cnt2 = torch.zeros((4,), dtype=torch.int32, device=dev)
         _lib.check(self._timed("select_rescore_retry", lambda: lib.hcir_select_rescore(
             q32_2.data_ptr(), self.g32.data_ptr(), self.ld, n_unc, self.n, k, self.idx_offset, plan, ws.data_ptr(),
             dq.data_ptr(), self.g_delta_max, self.eps_acc, o_s.data_ptr(), o_i.data_ptr(), unc2.data_ptr(),
-            cnt2.data_ptr(), st)), "select_rescore(retry)")
-        n2 = int(cnt2.item())
+            cnt2.data_ptr(), None, st)), "select_rescore(retry)")
+        n2 = int(cnt2[1].item())
         if n2 < n_unc:
             ok = torch.ones((n_unc,), dtype=torch.bool, device=dev)
             ok[unc2[:n2].long()] = False
@@ -530,6 +543,7 @@ def _gallery_from_parts(cls, g32, gbf, g_delta_max, d, labels, classes, device, 
     self.last_stats, self.retry_stats = {}, {}
     self.kernel_events = None
     self.launches = 0
+    self.k3_width = 0
     return self
 
 
@@ -539,12 +553,16 @@ GalleryBank._from_parts = classmethod(_gallery_from_parts)
 # ---------------------------------------------------------------------------------------------
 # functional surface
 # ---------------------------------------------------------------------------------------------
-def knn_topk(bank, query, k, *, mode: str = "auto"):
+def knn_topk(bank, query, k, *, normalized: bool = False, mode: str = "auto", use_graph: bool = False):
     """``torch.mm(query_n, bank_n.t()).topk(k)`` (qualitative_test.py:79-84;
     dual_view_model.py:317-335) without materialising the similarity matrix.
-    ``bank`` is a [N, D] array/tensor or a prepared :class:`GalleryBank`."""
+    ``bank`` is a [N, D] array/tensor or a prepared :class:`GalleryBank`.  ``normalized`` states
+    that the rows are already unit vectors, as at the reference's call sites (F.normalize at
+    qualitative_test.py:57,76); K1 normalises either way -- idempotent up to fp32 rounding -- because
+    the bf16 bank and the certification bound are produced by the same pass."""
+    del normalized
     gb = bank if isinstance(bank, GalleryBank) else GalleryBank(bank)
-    return gb.topk(query, k, mode=mode)
+    return gb.topk(query, k, mode=mode, use_graph=use_graph)
 
 
 def knn_predict(query, bank, labels, k, *, T=None, mode: str = "auto"):
@@ -586,35 +604,42 @@ class PendingStep:
 # ---------------------------------------------------------------------------------------------
 class SearchSession:
     """A fixed-shape search step (``nq`` queries, ``k`` neighbours, optional vote) captured ONCE
-    into a CUDA graph: K1(queries) -> K2 (sample pass, thresholds, main pass) -> K3 -> label gather
-    -> K4.  ``run`` copies the queries into the static input buffer, replays the graph (one launch
-    instead of ~12 launches and their host-side allocation / planning work) and reads back the
-    4-byte count of uncertified queries; those (rare) are finished eagerly by the exact kernel.
+    into a CUDA graph of FIVE kernels: K1(queries) -> K2 sample pass -> thresholds -> K2 main pass ->
+    K3 with its fused tail (neighbour labels, vote, stores into the peer regions).  No fill / copy
+    nodes: K3 maintains its own counters.  ``run`` copies the queries into the static input buffer,
+    replays the graph (one launch instead of a dozen launches and their host-side allocation /
+    planning work) and reads back the 4-byte count of uncertified queries; those (rare) are
+    finished eagerly by the second tensor pass / the exact kernel.
 
     Only the tensor path is captured; ``GalleryBank.session`` returns None when the bank would use
     the exact CUDA-core path for this shape.  ``profile=True`` adds external CUDA events around the
-    sample pass, the main pass and K3 so their durations can be read after every replay."""
+    sample pass, the main pass and K3 so their durations can be read after every replay.
+
+    Multi-GPU (sharded.py): ``tail_hook(session, tail)`` fills the peer fields of K3's tail (the
+    channel is allocated collectively on the eager warm-up pass); ``post(session)`` enqueues what
+    follows K3 in the same graph (the fused wait + merge + vote kernel, or the wait kernel)."""
 
     def __init__(self, bank: "GalleryBank", nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False,
-                 pack: bool = False, post=None):
+                 pack: bool = False, post=None, tail_hook=None, trailer: bool = False):
         if not (1 <= k <= bank.n):
             raise ValueError(f"k={k} must be in [1, N={bank.n}]")
         if vote and bank.labels is None:
             raise ValueError("this GalleryBank was built without labels")
         self.bank, self.nq, self.k, self.T, self.vote = bank, int(nq), int(k), T, vote
         # pack: results live in ONE byte block [idx | sims | labels] (hcir_packed_block_bytes), the
-        # unit of the multi-GPU candidate all-gather; out_sim / out_idx / out_lab are views of it
+        # unit of the NCCL candidate all-gather; out_sim / out_idx / out_lab are views of it
         self.pack_results = bool(pack)
-        # post(session): extra work captured at the end of the graph (multi-GPU: the candidate
-        # all-gather + merge + vote).  With it the packed block gets a 16-byte trailer holding this
-        # rank's uncertified count, and run(check=False) leaves the read-back to the caller.
-        self.post, self.post_out = post, None
-        self.trailer = 16 if (pack and post is not None) else 0
+        self.post, self.post_out, self.tail_hook = post, None, tail_hook
+        # trailer (NCCL exchange only): 16 bytes behind the packed block carry this rank's uncertified count
+        self.trailer = 16 if (pack and trailer) else 0
         dev = bank.device
         self.events = {}
         self._profile = profile
         with torch.cuda.device(dev):
             self.q_in = torch.zeros((self.nq, bank.d), dtype=torch.float32, device=dev)
+            # K3's counters: zero once, the kernel leaves [0] and [2] at zero after every launch
+            self.unc_state = torch.zeros((4,), dtype=torch.int32, device=dev)
+            self.unc_cnt = self.unc_state[1:2]   # result of the last launch
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -648,8 +673,8 @@ class SearchSession:
         self.plan = plan
         self.ws = torch.empty((int(plan.bytes),), dtype=torch.uint8, device=dev)
         self.out_lab = None
+        with_lab = b.labels is not None
         if self.pack_results:
-            with_lab = b.labels is not None
             e = nq * k
             self.block_bytes = int(lib.hcir_packed_block_bytes(nq, k, int(with_lab)))
             self.pack = torch.zeros((self.block_bytes + self.trailer,), dtype=torch.uint8, device=dev)
@@ -661,8 +686,7 @@ class SearchSession:
             self.out_sim = torch.empty((nq, k), dtype=torch.float32, device=dev)
             self.out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
         self.unc_list = torch.empty((nq,), dtype=torch.int32, device=dev)
-        self.unc_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
-        kernels = 1 + 1  # l2norm + the unc_cnt fill
+        kernels = 1  # l2norm
         self._mark("t0", capture)
         if plan.sample_rows > 0:
             plan.flags = 2
@@ -671,22 +695,35 @@ class SearchSession:
             self._mark("t1", capture)
             plan.flags = 4
             kernels += 2
+        # measurement aid: HCIR_MAIN_FLAGS=16 runs the main pass on CTA pairs (cta_group::2), 32 rotates tiles
+        plan.flags |= int(os.environ.get("HCIR_MAIN_FLAGS", "0")) & (16 | 32)
         _lib.check(lib.hcir_simtopk(self.qbf.data_ptr(), nq, b.gbf.data_ptr(), b.n, b.ld, plan,
                                     self.ws.data_ptr(), st), "simtopk(main)")
-        plan.flags = 0
+        plan.flags = b.k3_width << 8
         self._mark("t2", capture)
+        # K3 + tail: labels / vote / peers happen inside the query's own CTA
+        tail = Tail()
+        self.pred = None
+        if with_lab and (self.vote or self.out_lab is not None):
+            tail.labels, tail.n_labels = b.labels.data_ptr(), b.n
+            tail.num_classes = len(b.classes_)
+        if self.vote:
+            self.pred = torch.empty((nq,), dtype=torch.int64, device=dev)
+            tail.pred = self.pred.data_ptr()
+            tail.T = float(self.T) if self.T is not None else 0.0
+            tail.classes = b._classes_device().data_ptr()
+        if self.out_lab is not None:
+            tail.out_lab = self.out_lab.data_ptr()
+        if self.tail_hook is not None:
+            self.tail_hook(self, tail)
         _lib.check(lib.hcir_select_rescore(self.q32.data_ptr(), b.g32.data_ptr(), b.ld, nq, b.n, k, b.idx_offset,
                                            plan, self.ws.data_ptr(), self.qdl.data_ptr(), b.g_delta_max, b.eps_acc,
                                            self.out_sim.data_ptr(), self.out_idx.data_ptr(),
-                                           self.unc_list.data_ptr(), self.unc_cnt.data_ptr(), st), "select_rescore")
+                                           self.unc_list.data_ptr(), self.unc_state.data_ptr(), tail, st),
+                   "select_rescore")
+        plan.flags = 0
         self._mark("t3", capture)
         kernels += 2
-        self.pred = self._tail() if self.vote else None   # (packed results: also fills out_lab)
-        if self.vote:
-            kernels += 1
-        elif self.out_lab is not None:
-            self._gather_packed_labels()
-            kernels += 1
         if self.trailer:
             self.pack[self.block_bytes: self.block_bytes + 4].view(torch.int32).copy_(self.unc_cnt)
         if self.post is not None:
@@ -783,21 +820,36 @@ class SearchSession:
 
 
 def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False, pack: bool = False,
-                  post=None, post_key=None):
+                  post=None, post_key=None, tail_hook=None, trailer: bool = False):
     """Cached :class:`SearchSession` for this shape, or None if the exact path would be used."""
     if nq < 1 or not self.use_tensor_path(nq, k):
         return None
     key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile), bool(pack), post_key)
-    cache = self.__dict__.setdefault("_sessions", {})
+    # Sessions whose graph ends in a multi-GPU exchange own a collectively constructed channel: they
+    # live in their own cache, whose keys hold rank-independent values only, so every rank creates
+    # and evicts them at the same calls (rank-local sessions can never shift that order).
+    cache = self.__dict__.setdefault("_sessions_collective" if post is not None else "_sessions", {})
     s = cache.get(key)
     if s is None:
         if len(cache) >= 4:  # each session owns a workspace: keep a handful
             old = cache.pop(next(iter(cache)))
             xc = getattr(old, "xchg", None)
-            if xc is not None:   # multi-GPU: every rank evicts the same session at the same call -> collective close
+            if xc is not None:   # every rank evicts the same session at the same call -> collective close
                 xc.close()
-        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack, post=post)
+        s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack, post=post,
+                                       tail_hook=tail_hook, trailer=trailer)
     return s
 
 
+def _bank_drop_sessions(self):
+    """Forget every cached SearchSession (their CUDA graphs hold raw pointers into this bank's
+    tensors).  COLLECTIVE when sessions with a multi-GPU exchange exist: all ranks must call it."""
+    self.__dict__.pop("_sessions", None)
+    for sess in self.__dict__.pop("_sessions_collective", {}).values():
+        xc = getattr(sess, "xchg", None)
+        if xc is not None:
+            xc.close()
+
+
+GalleryBank.drop_sessions = _bank_drop_sessions
 GalleryBank.session = _bank_session

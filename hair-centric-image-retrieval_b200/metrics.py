@@ -50,14 +50,44 @@ def recall_ap_at_k(neighbour_idx, ground_truth, ks=(10, 20, 50)):
     return out
 
 
-def kth_neighbour(embeddings, k: int = 7, *, mode: str = "auto"):
-    """neg_sampling.py:26-53 with metric='cosine': ``sorted_indices[:, k-1]`` of the row-wise
-    descending sort of the batch similarity matrix.  Returns int64 [B] (same device kind as the
-    input).  Exact ties are ordered by ascending index (torch.sort leaves them unspecified)."""
+def kth_neighbour(embeddings, k: int = 7, *, metric: str = "cosine", mode: str = "auto"):
+    """``NegSamplerStatic`` (neg_sampling.py:26-53): ``sorted_indices[:, k-1]`` of the row-wise
+    descending sort of the batch similarity matrix -- cosine similarity of the rows (:34-37) or negative
+    euclidean distance of the RAW rows (:38-41).  Returns int64 [B] (same device kind as the input).
+    Exact ties are ordered by ascending index (torch.sort leaves them unspecified).
+
+    euclidean: for a fixed row a, ascending ||a - b|| == descending a.b - ||b||^2 / 2, an inner product
+    of the augmented rows [a, 1] . [b, -||b||^2 / 2]; the exact fp32 CUDA-core kernel ranks by that
+    inner product directly (it normalises nothing), so no second code path is needed."""
     x = embeddings if isinstance(embeddings, torch.Tensor) else torch.as_tensor(np.asarray(embeddings))
     b = x.shape[0]
     if k < 1 or k > b:
         raise ValueError(f"k must be between 1 and {b}")
-    bank = GalleryBank(x.detach().float())
-    _, idx = bank.topk(x.detach().float(), k, mode=mode)
-    return idx[:, k - 1]
+    if metric == "cosine":
+        bank = GalleryBank(x.detach().float())
+        _, idx = bank.topk(x.detach().float(), k, mode=mode)
+        return idx[:, k - 1]
+    if metric != "euclidean":
+        raise ValueError("Unsupported metric. Choose 'cosine' or 'euclidean'.")
+    from . import _lib
+    from .engine import _require_cuda, _sm_count, _stream_ptr
+    lib = _lib.load()
+    dev = x.device if x.is_cuda else _require_cuda(None)
+    with torch.cuda.device(dev):
+        xd = x.detach().to(dev, torch.float32)
+        d = xd.shape[1]
+        ld = lib.hcir_padded_dim(d + 1)
+        qa = torch.zeros((b, ld), dtype=torch.float32, device=dev)
+        ga = torch.zeros((b, ld), dtype=torch.float32, device=dev)
+        qa[:, :d], ga[:, :d] = xd, xd
+        qa[:, d] = 1.0
+        ga[:, d] = -0.5 * (xd.double() ** 2).sum(dim=1).float()
+        o_s = torch.empty((b, k), dtype=torch.float32, device=dev)
+        o_i = torch.empty((b, k), dtype=torch.int64, device=dev)
+        sms = _sm_count(dev)
+        nbytes = int(lib.hcir_exact_workspace_bytes(b, b, k, sms))
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.hcir_exact_topk(qa.data_ptr(), ga.data_ptr(), ld, b, k, 0, None, b, o_s.data_ptr(),
+                                       o_i.data_ptr(), ws.data_ptr(), nbytes, sms, _stream_ptr()), "exact_topk")
+        out = o_i[:, k - 1]
+        return out if x.is_cuda else out.cpu()

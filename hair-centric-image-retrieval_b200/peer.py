@@ -1,10 +1,13 @@
 """Exchange of per-rank result blocks over NVLink peer memory (csrc/peer.cu): the path's own
 all-gather.  Every rank stores its block straight into a slot of EVERY rank's region with plain
-16-byte stores (the regions are cudaMalloc'd by the library, exported with CUDA IPC and mapped by
-all ranks of the box), bumps an arrival counter behind a system-scope fence, and a one-warp kernel
-on each rank spins until all blocks of the step have landed.  No collective-library call sits on
-the data path, and because the step counter lives in device memory the push / wait pair is
-captured into the search step's CUDA graph and replayed unchanged.
+stores (the regions are cudaMalloc'd by the library, exported with CUDA IPC and mapped by all ranks
+of the box) and bumps an arrival counter behind a system-scope fence; the consumer kernel on each
+rank spins until all blocks of the step have landed.  In the search step the producer is the TAIL
+OF K3 (every query's CTA stores its own results into the peers: ``fill_tail``) and the consumer is
+the fused wait + merge + vote kernel (``hcir_peer_merge_vote``) or the one-warp wait kernel
+(``enqueue_wait``); ``exchange`` is the standalone push + wait for blocks that already sit in
+memory.  No collective-library call sits on the data path, and because the completed-step counter
+lives in device memory the exchange is captured into the step's CUDA graph and replayed unchanged.
 
 ``torch.distributed`` is used once, at construction, to trade the 64-byte IPC handles (SURVEY.md
 section 8e "later fusion"; no reference analogue -- the reference's kNN is single-process CPU)."""
@@ -83,8 +86,12 @@ class PeerExchange:
         self.stride = -(-self.slot_bytes // 256) * 256
         # how long a wait kernel spins for a late peer before it reports instead of hanging the GPU
         # (ranks of one job reach the same step seconds apart at most; HCIR_PEER_TIMEOUT_S overrides)
+        # 120 s by default: long enough for a peer that is finishing a batch of uncertified queries on
+        # the exact fp32 kernel or sitting in a debugger breakpoint-free stall, short enough not to
+        # look like a hung GPU.  After a timeout the channel is dead (the error word is sticky): the
+        # owner must close() it and build a new one -- ShardedGallery / QueryShardedGallery.close().
         if timeout_s is None:
-            timeout_s = float(os.environ.get("HCIR_PEER_TIMEOUT_S", "30"))
+            timeout_s = float(os.environ.get("HCIR_PEER_TIMEOUT_S", "120"))
         self.timeout_ns = int(timeout_s * 1e9)
         total = int(self.lib.hcir_peer_region_bytes(self.world, self.slot_bytes))
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -128,33 +135,48 @@ class PeerExchange:
             torch.cuda.synchronize(self.device)
         dist.barrier(group)   # every region is zeroed and mapped everywhere before the first push
         self.host_step = 0
-        self.ctas = 1
         self.block_bytes = None
         self._closed = False
 
     # ------------------------------------------------------------------ data path (capturable)
-    def exchange(self, block: torch.Tensor, meta: torch.Tensor | None = None):
-        """Enqueue: step += 1, push ``block`` (contiguous bytes, multiple of 16) + the int32 ``meta``
-        word into every rank's region, wait for every rank's block of this step."""
-        nbytes = block.numel() * block.element_size()
-        if not block.is_contiguous() or nbytes % 16 or nbytes > self.slot_bytes:
-            raise ValueError(f"peer exchange block must be contiguous, a multiple of 16 bytes and <= {self.slot_bytes}")
-        if self.block_bytes not in (None, nbytes):   # arrivals are counted per step: one block size per channel
+    def _check_block(self, nbytes: int):
+        if nbytes % 8 or nbytes > self.slot_bytes:
+            raise ValueError(f"peer exchange block must be a multiple of 8 bytes and <= {self.slot_bytes}")
+        if self.block_bytes not in (None, nbytes):   # one block shape per channel
             raise ValueError(f"peer exchange channel carries blocks of {self.block_bytes} bytes, got {nbytes}")
         self.block_bytes = nbytes
-        st = torch.cuda.current_stream().cuda_stream
-        self.step.add_(1)
-        self.ctas = int(self.lib.hcir_peer_push_ctas(nbytes))
-        _lib.check(self.lib.hcir_peer_push(block.data_ptr(), nbytes, self._regions, self.world, self.rank,
-                                           self.slot_bytes, self.step.data_ptr(),
-                                           meta.data_ptr() if meta is not None else None, st), "peer_push")
-        _lib.check(self.lib.hcir_peer_wait(self._local_ptr, self.world, self.step.data_ptr(), self.ctas,
-                                           self.timeout_ns, st), "peer_wait")
+
+    def fill_tail(self, tail, payload: int, nbytes: int):
+        """Make K3 the producer of this channel: the peer fields of an hcir_tail_t (_lib.Tail)."""
+        self._check_block(nbytes)
+        tail.world, tail.rank, tail.payload = self.world, self.rank, int(payload)
+        tail.slot_bytes = self.slot_bytes
+        for r, p in enumerate(self._ptrs):
+            tail.regions[r] = p
+        tail.step = self.step.data_ptr()
+
+    def enqueue_wait(self):
+        """Consumer, wait only: every rank's block of the step has landed; completes the step."""
+        _lib.check(self.lib.hcir_peer_wait(self._local_ptr, self.world, self.step.data_ptr(), self.timeout_ns,
+                                           torch.cuda.current_stream().cuda_stream), "peer_wait")
         if not torch.cuda.is_current_stream_capturing():
             self.host_step += 1
 
+    def exchange(self, block: torch.Tensor, meta: torch.Tensor | None = None):
+        """Standalone producer + consumer: push ``block`` (contiguous bytes, multiple of 16) + the
+        int32 ``meta`` word into every rank's region, wait for every rank's block of this step."""
+        nbytes = block.numel() * block.element_size()
+        if not block.is_contiguous() or nbytes % 16:
+            raise ValueError("peer exchange block must be contiguous and a multiple of 16 bytes")
+        self._check_block(nbytes)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.hcir_peer_push(block.data_ptr(), nbytes, self._regions, self.world, self.rank,
+                                           self.slot_bytes, self.step.data_ptr(),
+                                           meta.data_ptr() if meta is not None else None, st), "peer_push")
+        self.enqueue_wait()
+
     def note_replay(self):
-        """A CUDA graph holding one captured ``exchange`` was replayed."""
+        """A CUDA graph holding one captured step of this channel was replayed."""
         self.host_step += 1
 
     # ------------------------------------------------------------------ reading the result

@@ -144,31 +144,36 @@ class ShardedGallery:
             sims, idx = torch.cat([sims, pad_s], 1), torch.cat([idx, pad_i], 1)
         return sims, idx
 
-    def _post(self, sess, want_vote: bool, T):
-        return self._post_peer(sess, want_vote, T) if self.exchange == "peer" else self._post_nccl(sess, want_vote, T)
+    def _tail_peer(self, sess, tail):
+        """K3's tail as the producer of the exchange: every query's CTA stores its packed rows
+        (idx | sims | labels) into every rank's peer region over NVLink; the launch's last CTA sends
+        the uncertified count and the arrival signal.  The channel is allocated collectively on the
+        session's eager warm-up pass."""
+        xc = getattr(sess, "xchg", None)
+        if xc is None:
+            xc = sess.xchg = PeerExchange(sess.block_bytes, group=self.group, device=self.device)
+        xc.fill_tail(tail, _lib.PAYLOAD_BLOCK, sess.block_bytes)
 
     def _post_peer(self, sess, want_vote: bool, T):
-        """Tail of the step, captured into the same CUDA graph as the local search: this rank's packed
-        block is PUSHED into every rank's peer region over NVLink (its uncertified count rides along
-        as the meta word), a one-warp kernel waits for all blocks of the step, K5 reads them in
-        place, then (predict) the vote.  No collective-library call on the data path."""
+        """What follows K3 in the step's graph: ONE kernel that waits for all ranks' blocks of the
+        step, merges them in place (K5) and votes.  No collective-library call on the data path."""
         lib, dev = self.bank.lib, self.device
         nq, k = sess.nq, sess.k
         has_lab = sess.out_lab is not None
-        xc = getattr(sess, "xchg", None)
-        if xc is None:   # first (eager warm-up) pass of the session body: collective allocation
-            xc = sess.xchg = PeerExchange(sess.block_bytes, group=self.group, device=dev)
-        xc.exchange(sess.pack[: sess.block_bytes], meta=sess.unc_cnt)
+        xc = sess.xchg
         o_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
         o_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
         o_l = torch.empty((nq, k), dtype=torch.int32, device=dev) if has_lab else None
-        self.bank.launches += 3
-        _lib.check(lib.hcir_merge_topk_peer(xc.local_ptr, self.world, nq, k, int(has_lab), xc.slot_bytes,
-                                            xc.step.data_ptr(), o_s.data_ptr(), o_i.data_ptr(),
-                                            o_l.data_ptr() if has_lab else None, _stream_ptr()), "merge_topk_peer")
-        pred = None
-        if want_vote:
-            pred = self.bank.vote_from_labels(o_s, o_l, T=T)
+        pred = torch.empty((nq,), dtype=torch.int64, device=dev) if (want_vote and has_lab) else None
+        self.bank.launches += 1
+        _lib.check(lib.hcir_peer_merge_vote(
+            xc.local_ptr, self.world, nq, k, int(has_lab), xc.slot_bytes, xc.step.data_ptr(), xc.timeout_ns,
+            o_s.data_ptr(), o_i.data_ptr(), o_l.data_ptr() if has_lab else None,
+            len(self.bank.classes_) if pred is not None else 0, float(T) if T is not None else 0.0,
+            self.bank._classes_device().data_ptr() if pred is not None else None,
+            pred.data_ptr() if pred is not None else None, _stream_ptr()), "peer_merge_vote")
+        if not torch.cuda.is_current_stream_capturing():
+            xc.host_step += 1   # the eager warm-up pass completed a step
         return {"gathered": None, "xchg": xc, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
 
     def _post_nccl(self, sess, want_vote: bool, T):
@@ -193,11 +198,25 @@ class ShardedGallery:
             pred = self.bank.vote_from_labels(o_s, o_l, T=T)
         return {"gathered": gathered, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
 
+    def _packed_session(self, nq: int, k: int, want_vote: bool, T):
+        key = ("gallery-sharded", self.world, self.exchange, want_vote, None if T is None else float(T))
+        if self.exchange == "peer":
+            return self.bank.session(nq, k, vote=False, profile=self.profile, pack=True, tail_hook=self._tail_peer,
+                                     post=lambda s_: self._post_peer(s_, want_vote, T), post_key=key)
+        return self.bank.session(nq, k, vote=False, profile=self.profile, pack=True, trailer=True,
+                                 post=lambda s_: self._post_nccl(s_, want_vote, T), post_key=key)
+
+    def close(self):
+        """COLLECTIVE: drop the cached sessions and close their peer channels (IPC mappings, regions)."""
+        self.bank.drop_sessions()
+
+    def _check_k(self, k: int):
+        if not (1 <= int(k) <= self.plan.n):
+            raise ValueError(f"k={k} must be in [1, N={self.plan.n}]")
+
     def _step_packed(self, q: torch.Tensor, k: int, want_vote: bool, T):
         """Whole multi-GPU step as ONE graph launch per rank; None if the tensor path does not apply."""
-        key = ("gallery-sharded", self.exchange, want_vote, None if T is None else float(T))
-        sess = self.bank.session(q.shape[0], k, vote=False, profile=self.profile, pack=True,
-                                 post=lambda s_: self._post(s_, want_vote, T), post_key=key)
+        sess = self._packed_session(q.shape[0], k, want_vote, T)
         if sess is None or (want_vote and sess.out_lab is None):
             return None
         sess.run(q, check=False)
@@ -234,9 +253,7 @@ class ShardedGallery:
             GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world)))
         if ok:
             with torch.cuda.device(self.device):
-                key = ("gallery-sharded", self.exchange, True, None if T is None else float(T))
-                sess = self.bank.session(q.shape[0], int(k), vote=False, profile=self.profile, pack=True,
-                                         post=lambda s_: self._post(s_, True, T), post_key=key)
+                sess = self._packed_session(q.shape[0], int(k), True, T)
                 if sess is not None and sess.out_lab is not None:
                     sess.run(q, check=False)
                     self.last_session = sess
@@ -252,6 +269,7 @@ class ShardedGallery:
 
     def topk(self, queries, k: int, *, mode: str = "auto", with_labels: bool = False):
         q, kind = _as_2d_f32(queries, "queries")
+        self._check_k(k)
         with torch.cuda.device(self.device):
             if not q.is_cuda:
                 q = q.contiguous().to(self.device, non_blocking=True)
@@ -278,6 +296,7 @@ class ShardedGallery:
 
     def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
         q, kind = _as_2d_f32(queries, "queries")
+        self._check_k(k)
         packed_ok = mode == "auto" and q.shape[0] > 0 and self.bank.labels is not None and all(
             GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world))
         if packed_ok:
@@ -323,9 +342,13 @@ def gather_rows(local: torch.Tensor, sp: ShardPlan, group=None) -> torch.Tensor:
 
 class QueryShardedGallery:
     """Every rank holds the whole gallery; rank r answers the contiguous query slice
-    [ShardPlan(Q, world).start(r), stop(r)) and ONE all-gather returns everybody's answers to
-    every rank.  Results are bit-identical to the single-GPU result by construction (each query is
-    answered by exactly the single-GPU code path)."""
+    [ShardPlan(Q, world).start(r), stop(r)) and every rank receives everybody's answers.  Results are
+    bit-identical to the single-GPU result by construction (each query is answered by exactly the
+    single-GPU code path).
+
+    Exchange "peer": the step is ONE graph launch per rank -- K3's tail stores each query's
+    prediction (``predict``) or packed top-k rows (``topk``) straight into every rank's peer region
+    and a one-warp kernel waits for the other ranks' blocks; "nccl": one all-gather per result array."""
 
     def __init__(self, features, labels=None, *, group=None, device=None, classes=None, exchange: str | None = None):
         self.group = group
@@ -344,29 +367,50 @@ class QueryShardedGallery:
     def _gather_rows(self, local: torch.Tensor, sp: ShardPlan) -> torch.Tensor:
         return gather_rows(local, sp, self.group)
 
-    def _post_peer(self, sess, hmax: int):
-        """Captured at the end of the local step's graph: this rank's predictions are pushed into
-        every rank's peer region over NVLink (uncertified count as the meta word) and a one-warp
-        kernel waits for everybody's block."""
-        nwords = -(-hmax // 2) * 2   # 16-byte multiple
+    def _tail_peer(self, sess, tail, payload: int, nbytes: int):
+        """K3's tail as the producer: every query's CTA stores its prediction (or its packed top-k
+        rows) into every rank's peer region over NVLink; the last CTA signals arrival."""
         xc = getattr(sess, "xchg", None)
         if xc is None:   # eager warm-up pass of the session body: collective allocation
-            xc = sess.xchg = PeerExchange(nwords * 8, group=self.group, device=self.device)
-        blk = torch.zeros((nwords,), dtype=torch.int64, device=self.device)
-        blk[: sess.nq].copy_(sess.pred)
-        self.bank.launches += 2
-        xc.exchange(blk.view(torch.uint8), meta=sess.unc_cnt)
-        return {"xchg": xc}
+            xc = sess.xchg = PeerExchange(-(-nbytes // 16) * 16, group=self.group, device=self.device)
+        xc.fill_tail(tail, payload, nbytes)
 
-    def _issue_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
+    def _post_peer(self, sess):
+        """Captured behind K3: a one-warp kernel waits for everybody's block and completes the step."""
+        self.bank.launches += 1
+        sess.xchg.enqueue_wait()
+        return {"xchg": sess.xchg}
+
+    def close(self):
+        """COLLECTIVE: drop the cached sessions and close their peer channels (IPC mappings, regions)."""
+        self.bank.drop_sessions()
+
+    def _issue_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T, want: str = "pred"):
         """Enqueue the whole step (one graph launch per rank incl. the result exchange); None if the
-        tensor path does not apply.  -> (session, exchange, sizes, hmax)"""
+        tensor path does not apply.  -> (session, exchange, sizes, hmax)
+
+        Every rank captures the SAME shape: its slice padded to ``hmax`` rows (slices differ by at
+        most one row; the pad repeats the rank's last query and its answer is dropped).  The cached
+        session -- and the collectively constructed PeerExchange it owns -- is therefore keyed on
+        rank-independent values only, so all ranks hit or miss the cache together (a per-rank slice
+        height in the key let Q=1024 then Q=1023 on 8 ranks desynchronise: seven ranks replayed the old
+        graph while the eighth entered a collective allocation alone)."""
         sizes = [sp.size(r) for r in range(self.world)]
-        if min(sizes) < 1 or not self.bank.use_tensor_path(mine.shape[0], k):   # same decision on every rank
-            return None
         hmax = max(sizes)
-        sess = self.bank.session(mine.shape[0], k, T=T, profile=self.profile,
-                                 post=lambda s_: self._post_peer(s_, hmax), post_key=("query-sharded", hmax))
+        if min(sizes) < 1 or not self.bank.use_tensor_path(hmax, k):   # same decision on every rank
+            return None
+        if want == "pred" and self.bank.labels is None:
+            raise ValueError("this gallery was built without labels")
+        if mine.shape[0] < hmax:
+            mine = torch.cat([mine, mine[-1:].expand(hmax - mine.shape[0], -1)], 0)
+        if want == "pred":
+            sess = self.bank.session(hmax, k, T=T, profile=self.profile,
+                                     tail_hook=lambda s_, t_: self._tail_peer(s_, t_, _lib.PAYLOAD_PRED, hmax * 8),
+                                     post=self._post_peer, post_key=("query-sharded", self.world, hmax))
+        else:
+            sess = self.bank.session(hmax, k, vote=False, pack=True, profile=self.profile,
+                                     tail_hook=lambda s_, t_: self._tail_peer(s_, t_, _lib.PAYLOAD_BLOCK, s_.block_bytes),
+                                     post=self._post_peer, post_key=("query-sharded-topk", self.world, hmax))
         if sess is None:
             return None
         sess.run(mine, check=False)
@@ -381,41 +425,74 @@ class QueryShardedGallery:
             return g.reshape(-1).view(torch.int64).clone()   # the region is reused two steps later
         return torch.cat([g[r, : sizes[r] * 8].contiguous().view(torch.int64) for r in range(self.world)], 0)
 
-    def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:
-        """Pipelined ``predict`` for DEVICE queries (see ShardedGallery.submit_predict)."""
-        q, kind = _as_2d_f32(queries, "queries")
-        if self.exchange == "peer" and q.is_cuda:
-            sp, mine = self._slice(q)
-            with torch.cuda.device(self.device):
-                issued = self._issue_peer(mine, sp, int(k), T)
-                if issued is not None:
-                    sess, xc, sizes, hmax = issued
-                    slot, step = xc.header_async()
-                    pred = self._gathered_preds(xc, sizes, hmax)
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), pred,
-                                       lambda: self.predict(q, k, T=T))
-        return PendingStep(None, None, None, self.predict(queries, k, T=T), None)
+    def _gathered_topk(self, xc, sizes, hmax, k):
+        """(sims [Q, k], idx [Q, k]) from the packed blocks (idx | sims [| labels]) of all ranks."""
+        g = xc.gathered()
+        e = hmax * k
+        idx = torch.cat([g[r, : e * 8].view(torch.int64).view(hmax, k)[: sizes[r]] for r in range(self.world)], 0)
+        sims = torch.cat([g[r, e * 8: e * 12].view(torch.float32).view(hmax, k)[: sizes[r]] for r in range(self.world)], 0)
+        return sims, idx   # torch.cat copies: the region is reused two steps later
 
-    def _predict_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
-        """Whole step = one graph launch per rank incl. the result exchange; None if not applicable."""
-        issued = self._issue_peer(mine, sp, k, T)
-        if issued is None:
-            return None
-        sess, xc, sizes, hmax = issued
-        counts = xc.metas()
+    def _stats(self, sess, counts):
         self.bank.last_stats = {"path": "tensor+graph", "uncertified": int(sum(counts)),
                                 "nsplit": int(sess.plan.nsplit), "kc": int(sess.plan.kc), "cap": int(sess.plan.cap),
                                 "workspace_bytes": int(sess.plan.bytes), "sample_rows": int(sess.plan.sample_rows),
                                 "chunk_w": int(sess.plan.chunk_w), "exchange": "peer"}
+
+    def _submit(self, queries, k: int, T, want: str) -> PendingStep:
+        q, kind = _as_2d_f32(queries, "queries")
+        sync = (lambda: self.predict(q, k, T=T)) if want == "pred" else (lambda: self.topk(q, k))
+        if self.exchange == "peer" and q.is_cuda:
+            sp, mine = self._slice(q)
+            with torch.cuda.device(self.device):
+                issued = self._issue_peer(mine, sp, int(k), T, want)
+                if issued is not None:
+                    sess, xc, sizes, hmax = issued
+                    slot, step = xc.header_async()
+                    res = self._gathered_preds(xc, sizes, hmax) if want == "pred" else \
+                        self._gathered_topk(xc, sizes, hmax, int(k))
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
+        return PendingStep(None, None, None, sync(), None)
+
+    def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:
+        """Pipelined ``predict`` for DEVICE queries (see ShardedGallery.submit_predict)."""
+        return self._submit(queries, k, T, "pred")
+
+    def submit_topk(self, queries, k: int) -> PendingStep:
+        """Pipelined ``topk`` for DEVICE queries: ``result()`` -> (sims, idx) on the device."""
+        return self._submit(queries, k, None, "topk")
+
+    def _predict_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T):
+        """Whole step = one graph launch per rank incl. the result exchange; None if not applicable."""
+        issued = self._issue_peer(mine, sp, k, T, "pred")
+        if issued is None:
+            return None
+        sess, xc, sizes, hmax = issued
+        counts = xc.metas()
+        self._stats(sess, counts)
         if any(c > 0 for c in counts):   # rare: every rank takes the completion + collective gather
             pred = sess.pred
             if counts[self.rank] > 0:
                 sess.finish_uncertified(counts[self.rank])
                 pred = sess._tail()
-            return self._gather_rows(pred, sp)
+            return self._gather_rows(pred[: sizes[self.rank]], sp)   # the session batch is padded to hmax
         return self._gathered_preds(xc, sizes, hmax)
+
+    def _topk_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int):
+        issued = self._issue_peer(mine, sp, k, None, "topk")
+        if issued is None:
+            return None
+        sess, xc, sizes, hmax = issued
+        counts = xc.metas()
+        self._stats(sess, counts)
+        if any(c > 0 for c in counts):   # rare: every rank takes the completion + collective gathers
+            if counts[self.rank] > 0:
+                sess.finish_uncertified(counts[self.rank])
+            n = sizes[self.rank]
+            return self._gather_rows(sess.out_sim[:n].contiguous(), sp), self._gather_rows(sess.out_idx[:n].contiguous(), sp)
+        return self._gathered_topk(xc, sizes, hmax, k)
 
     def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
         q, kind = _as_2d_f32(queries, "queries")
@@ -444,8 +521,12 @@ class QueryShardedGallery:
         with torch.cuda.device(self.device):
             if not mine.is_cuda:
                 mine = mine.contiguous().to(self.device, non_blocking=True)
-            sims, idx = self.bank._topk_device(mine, int(k), mode)
-            o_s, o_i = self._gather_rows(sims, sp), self._gather_rows(idx, sp)
+            out = self._topk_peer(mine, sp, int(k)) if (self.exchange == "peer" and mode == "auto") else None
+            if out is not None:
+                o_s, o_i = out
+            else:
+                sims, idx = self.bank._topk_device(mine, int(k), mode)
+                o_s, o_i = self._gather_rows(sims, sp), self._gather_rows(idx, sp)
         if kind == "torch_cuda":
             return o_s, o_i
         return _to_host(o_s, kind), _to_host(o_i, kind)

@@ -35,7 +35,7 @@ extern "C" {
 #define HCIR_ECUDA (-3)      /* a CUDA runtime / driver call failed                        */
 #define HCIR_EWORKSPACE (-4) /* workspace too small                                        */
 
-#define HCIR_ABI_VERSION 4
+#define HCIR_ABI_VERSION 5
 
 /* hcir_plan_t.flags: measurement aids, all 0 in production */
 #define HCIR_FLAG_NO_EMIT 1     /* main pass emits nothing: pure contraction throughput        */
@@ -43,6 +43,8 @@ extern "C" {
 #define HCIR_FLAG_MAIN_ONLY 4   /* enqueue only the main pass (thr0 already in the workspace)  */
 #define HCIR_FLAG_ROTATE 32     /* main pass: units start their gallery walk at staggered tiles */
 #define HCIR_FLAG_CTA_PAIRS 16  /* main pass on CTA pairs: tcgen05.mma.cta_group::2, 256x256 tile */
+#define HCIR_FLAG_K3_WIDTH_SHIFT 8 /* hcir_select_rescore CTA width: 0 = chosen from the shape,          */
+#define HCIR_FLAG_K3_WIDTH_MASK 0x300 /* 1 = 128, 2 = 256, 3 = 1024 threads per query (A/B measurement) */
 
 typedef void* hcir_stream_t; /* cudaStream_t */
 
@@ -120,23 +122,56 @@ int hcir_simtopk_debug(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf1
                        int ld, const hcir_plan_t* plan, void* workspace, float* scores,
                        hcir_stream_t stream);
 
-/* K3 -- candidate selection + fp32 re-score + exact sort + certification.  Replaces
- * torch.topk(sim, k) (qualitative_test.py:82), np.argsort(s)[::-1][:k]
- * (hair_encoder.py:194) and sklearn's argpartition+argsort (_kneighbors_reduce_func).
- * Per query: stream the split lists, keep the kc best by bf16 score, re-score with the
+/* K3 -- candidate selection + fp32 re-score + exact sort + certification, and the fused TAIL of the
+ * step.  Replaces torch.topk(sim, k) (qualitative_test.py:82), np.argsort(s)[::-1][:k]
+ * (hair_encoder.py:194) and sklearn's argpartition+argsort (_kneighbors_reduce_func); the tail
+ * replaces sklearn's `_mode(_y[neigh_ind])` vote (classification_engine.py:82) for single-GPU steps.
+ * Per query (one CTA): stream the split lists, keep the kc best by bf16 score, re-score with the
  * canonical fp32 dot product only the candidates that can still reach the top-k, emit the
  * exact top-k in canonical order, and certify it:
- *     certified <=> (all gallery rows were candidates) or
- *                   fp32_score(k-th) > t' + eps(query),
- *     t' = max(bf16_score(kc-th best candidate), largest list threshold)
+ *     certified <=> fp32_score(k-th) > t' + eps(query),
+ *     t' = max(largest list threshold, bf16 score of the kc-th best candidate when any listed
+ *          candidate was left out of the kc best)
  *     eps = g_delta_max*(1+q_delta) + q_delta*(1+1e-6) + eps_acc
- * Uncertified queries are appended to uncert_list / *uncert_count for hcir_exact_topk.
- *   out_sim [nq,k] fp32 descending, out_idx [nq,k] int64 (= local row + idx_offset). */
+ * Uncertified queries are appended to uncert_list for the completion pass / hcir_exact_topk.
+ *   out_sim [nq,k] fp32 descending, out_idx [nq,k] int64 (= local row + idx_offset).
+ *   uncert_state  int32[4], all zero before the first launch, maintained by the kernel:
+ *                 [0] running count (0 again when the launch ends), [1] RESULT: uncertified queries
+ *                 of the last launch, [2] done-CTA counter (0 again when the launch ends).
+ *                 No memset between launches: a captured step has no fill node.
+ *   tail (nullable) what every query's CTA does with its finished top-k:
+ *     labels != NULL   gather the neighbours' class indices (labels[row], row = LOCAL gallery row)
+ *                      -> out_lab [nq,k] (nullable)
+ *     pred != NULL     kNN vote (T <= 0 uniform, T > 0 temperature; hcir_vote's arithmetic and tie
+ *                      rule) -> pred[q] = classes[best] (class index when classes is NULL)
+ *     world > 0        multi-GPU: store the query's results into slot (parity of step *step + 1,
+ *                      rank) of EVERY peer region (hcir_peer_* below) over NVLink --
+ *                      payload 1: the packed block rows idx | sims | labels (hcir_packed_block_bytes
+ *                      layout), payload 2: the int64 prediction -- and let the LAST CTA of the launch
+ *                      write this rank's uncertified count as the meta word and bump
+ *                      arrivals[rank] once in every region.  No staging copy, no push kernel. */
+#define HCIR_PEER_MAX 16
+typedef struct {
+  const int32_t* labels;   /* [n_labels] class indices of the LOCAL gallery rows (nullable)         */
+  int64_t n_labels;
+  int32_t num_classes;
+  float T;
+  const int64_t* classes;  /* [num_classes] class values (nullable)                                */
+  int64_t* pred;           /* [nq] (nullable)                                                      */
+  int32_t* out_lab;        /* [nq,k] (nullable)                                                    */
+  int32_t world, rank;     /* world == 0: single GPU, nothing below is read                        */
+  int32_t payload;         /* 1 = packed block rows, 2 = predictions                               */
+  int32_t reserved_;
+  uint64_t slot_bytes;     /* the channel's slot size (hcir_peer_region_bytes)                      */
+  void* regions[HCIR_PEER_MAX]; /* every rank's region as mapped HERE, own region included          */
+  const int64_t* step;     /* the channel's completed-step counter (device)                        */
+} hcir_tail_t;
+
 int hcir_select_rescore(const float* q_f32, const float* g_f32, int ld, int64_t nq, int64_t ng,
                         int k, int64_t idx_offset, const hcir_plan_t* plan, const void* workspace,
                         const float* q_delta, float g_delta_max, float eps_acc, float* out_sim,
-                        int64_t* out_idx, int32_t* uncert_list, int32_t* uncert_count,
-                        hcir_stream_t stream);
+                        int64_t* out_idx, int32_t* uncert_list, int32_t* uncert_state,
+                        const hcir_tail_t* tail, hcir_stream_t stream);
 
 /* Exact fp32 path (CUDA cores): brute-force canonical fp32 similarities + exact top-k in
  * canonical order for the queries listed in qlist[0..nlist) (qlist == NULL: queries
@@ -199,16 +234,22 @@ int hcir_merge_topk_packed(const void* gathered, int G, int64_t nq, int k, int w
  * SURVEY.md section 8e "later fusion") ------------------------------------------------------
  * One REGION of device memory per rank, exported with CUDA IPC and mapped by every other rank of
  * the box; layout: 512-byte header (arrival counters, one int64 "meta" word per rank and parity,
- * last completed step, error word) + 2 parities x world slots of round_up(slot_bytes, 256).
+ * last completed step, error word, done-CTA counters) + 2 parities x world slots of
+ * round_up(slot_bytes, 256).  `step` is a device int64 per channel counting COMPLETED steps: the
+ * producer of step st = *step + 1 fills slot (st & 1, rank) of every region and bumps arrivals[rank]
+ * once everywhere; the consumer waits for arrivals[r] >= st for all r and writes *step = st.
  *   hcir_peer_alloc   cudaMalloc + zero + IPC export (64-byte handle) of this rank's region
  *   hcir_peer_open    map a peer's region from its handle;  hcir_peer_close / hcir_peer_free undo
- *   hcir_peer_push    store `bytes` (multiple of 16) of this rank's block into slot (step&1, rank) of
- *                     EVERY region in regions[0..world) (host array; own region included), plus the
- *                     int32 at meta_src (nullable) as this rank's meta word, then signal arrival.
- *                     `step` is a device int64 the caller increments on the stream before the push.
- *   hcir_peer_wait    spin (bounded by timeout_ns; on expiry header word 49 is set to the step)
- *                     until every rank's block of this step has landed in the LOCAL region
- *   hcir_merge_topk_peer   K5 reading this step's gathered blocks in place from the local region */
+ *   producer          normally the tail of hcir_select_rescore (every query's CTA stores its own
+ *                     results into the peers); hcir_peer_push is the standalone form: store `bytes`
+ *                     (multiple of 16) of a block that sits in memory into every region in
+ *                     regions[0..world) (host array; own region included) + the int32 at meta_src
+ *                     (nullable) as this rank's meta word, then signal arrival
+ *   hcir_peer_wait    consumer, wait only: spin (bounded by timeout_ns; on expiry header word 49 is
+ *                     set to the step) until every rank's block of the step has landed in the LOCAL
+ *                     region, then complete the step
+ *   hcir_peer_merge_vote   consumer of packed blocks, ONE kernel: wait as above, K5-merge the G
+ *                     blocks in place, vote on the merged labels (pred nullable), complete the step */
 size_t hcir_peer_region_bytes(int world, size_t slot_bytes);
 size_t hcir_peer_slot_offset(int world, size_t slot_bytes, int parity, int rank);
 int hcir_peer_push_ctas(size_t bytes);
@@ -219,11 +260,12 @@ int hcir_peer_free(void* ptr);
 int hcir_peer_push(const void* src, size_t bytes, void* const* regions, int world, int rank,
                    size_t slot_bytes, const int64_t* step, const int32_t* meta_src,
                    hcir_stream_t stream);
-int hcir_peer_wait(void* region_local, int world, const int64_t* step, int ctas_per_push,
-                   int64_t timeout_ns, hcir_stream_t stream);
-int hcir_merge_topk_peer(const void* region_local, int G, int64_t nq, int k, int with_labels,
-                         size_t slot_bytes, const int64_t* step, float* out_sim, int64_t* out_idx,
-                         int32_t* out_lab, hcir_stream_t stream);
+int hcir_peer_wait(void* region_local, int world, int64_t* step, int64_t timeout_ns,
+                   hcir_stream_t stream);
+int hcir_peer_merge_vote(void* region_local, int G, int64_t nq, int k, int with_labels,
+                         size_t slot_bytes, int64_t* step, int64_t timeout_ns, float* out_sim,
+                         int64_t* out_idx, int32_t* out_lab, int num_classes, float T,
+                         const int64_t* classes, int64_t* pred, hcir_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,8 @@ def main():
                 assert torch.equal(p, p_ref), (tag, exchange, "query predict", rep)
                 p = qg.predict(qs.cuda(), k)
                 assert torch.equal(p.cpu(), p_ref), (tag, exchange, "query predict (device queries)", rep)
+                s, i = qg.topk(qs, k)          # retrieval through the replicas: packed rows travel over the peers
+                assert torch.equal(i, i_ref) and torch.equal(s, s_ref), (tag, exchange, "query topk", rep)
             if exchange == "peer":   # pipelined submission: two steps in flight, checks read one step late
                 qc = qs.cuda()
                 for obj in (gal, qg):
@@ -59,6 +61,12 @@ def main():
                     for h in pend:
                         assert torch.equal(h.result().cpu(), p_ref), (tag, "submit_predict", type(obj).__name__)
                         assert h.redone == bool(expect_uncertified), (tag, "redone", type(obj).__name__)
+                pend = [qg.submit_topk(qc, k), qg.submit_topk(qc, k)]
+                for h in pend:
+                    s, i = h.result()
+                    assert torch.equal(i.cpu(), i_ref) and torch.equal(s.cpu(), s_ref), (tag, "submit_topk")
+                pt_ref = ref.predict(qs, k, T=0.07)   # the temperature vote through both partitions
+                assert torch.equal(gal.predict(qs, k, T=0.07), pt_ref) and torch.equal(qg.predict(qs, k, T=0.07), pt_ref)
             checks += 1
             del gal, qg
         del ref
@@ -84,6 +92,16 @@ def main():
                          device=dev, classes=ref.classes_, exchange="peer")
     for nq in (129, 130, 131, 132, 133, 134):
         assert torch.equal(gal.predict(qs[:nq], 20), ref.predict(qs[:nq], 20)), ("eviction", nq)
+    checks += 1
+
+    # batch sizes whose per-rank split differs (1024 -> 128 rows everywhere, 1023 -> one
+    # rank gets 127) on the SAME object must not desynchronise the ranks' session caches
+    qg = QueryShardedGallery(bank, bl, device=dev, classes=ref.classes_, exchange="peer")
+    big, _ = synth.make_clustered(1024, 256, 13, 93)
+    for nq in (1024, 1023, 1024, 1022, 1023):
+        assert torch.equal(qg.predict(big[:nq], 20), ref.predict(big[:nq], 20)), ("ragged replay", nq)
+    qg.close()
+    gal.close()
     checks += 1
 
     torch.cuda.synchronize()

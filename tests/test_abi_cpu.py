@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_builds_and_loads():
     lib = _lib.load()
     assert os.path.exists(_build.LIB_PATH)
-    assert lib.hcir_abi_version() == 4
+    assert lib.hcir_abi_version() == 5
     assert lib.hcir_padded_dim(768) == 768 and lib.hcir_padded_dim(512) == 512
     assert lib.hcir_padded_dim(100) == 128 and lib.hcir_padded_dim(2048) == 2048
 
@@ -149,8 +149,27 @@ def test_peer_region_layout_and_argument_validation():
     assert 1 <= lib.hcir_peer_push_ctas(10000 * 8) <= 64
     # null pointers / bad ranks are rejected before any CUDA call
     assert lib.hcir_peer_push(None, 16, None, 2, 0, 16, None, None, None) == _lib.HCIR_EINVAL
-    assert lib.hcir_peer_wait(None, 2, None, 1, 0, None) == _lib.HCIR_EINVAL
-    assert lib.hcir_merge_topk_peer(None, 2, 4, 3, 1, 1024, None, None, None, None, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_peer_wait(None, 2, None, 0, None) == _lib.HCIR_EINVAL
+    assert lib.hcir_peer_merge_vote(None, 2, 4, 3, 1, 1024, None, 0, None, None, None, 0, 0.0, None, None,
+                                    None) == _lib.HCIR_EINVAL
+    # K3's tail: a vote without labels, a peer tail without a step counter, a slot smaller than the block
+    plan = _lib.Plan()
+    assert lib.hcir_simtopk_plan(64, 100000, 768, 104, 148, plan) == 0
+    one = ctypes.c_void_p(16)   # any non-null pointer: validation happens before any CUDA call
+    def k3(tail):
+        return lib.hcir_select_rescore(one, one, 768, 64, 100000, 20, 0, plan, one, None, 0.0, 0.0, one, one, one, one,
+                                       tail, None)
+    t = _lib.Tail()
+    t.pred = 16
+    assert k3(t) == _lib.HCIR_EINVAL and "vote needs labels" in _lib.last_error()
+    t = _lib.Tail()
+    t.world, t.rank, t.payload = 2, 0, _lib.PAYLOAD_BLOCK
+    assert k3(t) == _lib.HCIR_EINVAL and "step counter" in _lib.last_error()
+    t.step, t.slot_bytes = 16, 64
+    assert k3(t) == _lib.HCIR_EINVAL and "smaller than" in _lib.last_error()
+    t = _lib.Tail()
+    t.world, t.rank = 2, 2
+    assert k3(t) == _lib.HCIR_EINVAL and "bad tail rank" in _lib.last_error()
     assert lib.hcir_vote_idx(None, None, None, 4, 0, 4, 0, 3, 0.0, None, None, None, None) == _lib.HCIR_EINVAL
 
 
