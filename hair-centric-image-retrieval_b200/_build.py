@@ -16,7 +16,7 @@ STAMP = os.path.join(HERE, "build", "stamp.txt")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("HCIR_NVCC_EXTRA", "").split()   # A/B builds on the GPU box (e.g. -DHCIR_DOT_GROUP=2)
 
 
 def _nvcc() -> str:

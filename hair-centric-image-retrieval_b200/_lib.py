@@ -17,7 +17,7 @@ class Plan(C.Structure):
     _fields_ = [("nsplit", C.c_int32), ("cap", C.c_int32), ("kc", C.c_int32), ("flags", C.c_int32),
                 ("sample_rows", C.c_int32), ("sample_stride", C.c_int32), ("chunk_w", C.c_int32),
                 ("num_chunks", C.c_int32), ("sample_nsplit", C.c_int32), ("nlists", C.c_int32),
-                ("hint_rank", C.c_int32), ("q_rows", C.c_int32),
+                ("hint_rank", C.c_int32), ("q_rows", C.c_int32), ("thr_rank", C.c_int32), ("reserved_", C.c_int32),
                 ("counts_off", C.c_uint64), ("thr_out_off", C.c_uint64), ("thr0_off", C.c_uint64),
                 ("thr_hi_off", C.c_uint64), ("cmax_off", C.c_uint64), ("keys_off", C.c_uint64),
                 ("bytes", C.c_uint64)]

@@ -99,24 +99,43 @@ __device__ __forceinline__ float canonical_dot(const float4* __restrict__ q4,
   return acc;
 }
 
-// Two rows at once (same per-row arithmetic order as canonical_dot, so bit-identical results):
-// twice the loads in flight per lane for the latency-bound row gathers of the re-score.
+// Two rows at once (same per-row arithmetic order as canonical_dot, so bit-identical results).  The row
+// gathers of the re-score are latency-bound: the loads of kDotGroup consecutive chunks of BOTH rows
+// (2 * kDotGroup independent 16-byte loads per lane) are issued before any is consumed, so a warp keeps
+// 3 KiB in flight instead of whatever the compiler's unrolling happens to stagger.
+#ifndef HCIR_DOT_GROUP
+#define HCIR_DOT_GROUP 3
+#endif
+constexpr int kDotGroup = HCIR_DOT_GROUP;
 __device__ __forceinline__ void canonical_dot2(const float4* __restrict__ q4, const float4* __restrict__ ga,
                                                const float4* __restrict__ gb, int ld4, int lane, float& sa,
                                                float& sb) {
   float a = 0.0f, b = 0.0f;
-  for (int c = lane; c < ld4; c += kWarp) {
-    const float4 x = q4[c];
-    const float4 y = __ldg(ga + c);
-    const float4 z = __ldg(gb + c);
-    a = fmaf(x.x, y.x, a);
-    a = fmaf(x.y, y.y, a);
-    a = fmaf(x.z, y.z, a);
-    a = fmaf(x.w, y.w, a);
-    b = fmaf(x.x, z.x, b);
-    b = fmaf(x.y, z.y, b);
-    b = fmaf(x.z, z.z, b);
-    b = fmaf(x.w, z.w, b);
+  for (int c0 = lane; c0 < ld4; c0 += kWarp * kDotGroup) {
+    float4 y[kDotGroup], z[kDotGroup];
+#pragma unroll
+    for (int u = 0; u < kDotGroup; ++u) {
+      const int c = c0 + u * kWarp;
+      if (c < ld4) {
+        y[u] = __ldg(ga + c);
+        z[u] = __ldg(gb + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kDotGroup; ++u) {
+      const int c = c0 + u * kWarp;
+      if (c < ld4) {
+        const float4 x = q4[c];
+        a = fmaf(x.x, y[u].x, a);
+        a = fmaf(x.y, y[u].y, a);
+        a = fmaf(x.z, y[u].z, a);
+        a = fmaf(x.w, y[u].w, a);
+        b = fmaf(x.x, z[u].x, b);
+        b = fmaf(x.y, z[u].y, b);
+        b = fmaf(x.z, z[u].z, b);
+        b = fmaf(x.w, z[u].w, b);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

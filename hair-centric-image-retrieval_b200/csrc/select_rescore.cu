@@ -25,17 +25,18 @@ constexpr int kRound1Slack = 6;
 constexpr int kBins = 2048;  // histogram bins of the fallback streaming selection
 
 struct SelSmem {  // offsets (bytes) into dynamic shared memory
-  size_t stage, sel, fk, qrow, hist, offs, scratch, total;
+  size_t stage, sel, fk, clab, qrow, hist, offs, scratch, total;
   int stage_cap;
 };
 
 static SelSmem sel_smem_layout(int nlists, int kc, int ld) {
   SelSmem L;
-  L.stage_cap = (8 * kc > 1024) ? 8 * kc : 1024;
+  L.stage_cap = (10 * kc > 1024) ? 10 * kc : 1024;  // the lists hold ~6.5 x kc keys (optimistic threshold): stage them all
   size_t o = 0;
   L.stage = o; o += static_cast<size_t>(L.stage_cap) * 8;
   L.sel = o; o += static_cast<size_t>(kc) * 8;
   L.fk = o; o += static_cast<size_t>(kc) * 8;
+  L.clab = o; o += static_cast<size_t>(kc) * 4;
   L.qrow = o; o += static_cast<size_t>(ld) * 4;
   L.hist = o; o += kBins * 4;
   L.offs = o; o += (static_cast<size_t>(nlists) + 1) * 4;
@@ -62,7 +63,10 @@ struct TailParams {
 
 // Visit every candidate key of this query in batches: the lists of warp w (w, w+W, ...) form a queue
 // of 32-key chunks; every round takes the next kKeyBatch chunks, issues all their loads, then hands
-// the batch to the visitor (kk[u] == 0: no key; RAW keys, their index part is never 0).
+// the batch to the visitor (kk[u] == 0: no key; RAW keys, their index part is never 0).  With the
+// optimistic main-pass threshold a query's lists hold 4-7 x kc keys in all -- a few dozen per list, a
+// handful in the streaming regime -- so a warp that walked one list per round trip (the round-1 walk,
+// 5 % faster on the long lists of the deterministic threshold) would pay one DRAM latency per list.
 constexpr int kKeyBatch = 8;
 template <int kSelThreads, typename F>
 __device__ __forceinline__ void for_each_batch(const uint64_t* __restrict__ lists, const int32_t* cnts, int nlists,
@@ -156,8 +160,11 @@ __device__ __forceinline__ void rank_scatter(const uint64_t* keys, int n, uint64
 // kSelThreads: 128 threads x 10 CTAs/SM (k <= 32, many queries: twice as many queries in flight hide the
 // barrier / gather latencies), 256 x 5 in general, 1024 for few queries (streaming regime: the per-query
 // latency IS the kernel time, so the whole CTA width goes to one query).
+#ifndef HCIR_K3_THREADS_PER_SM
+#define HCIR_K3_THREADS_PER_SM 1024  // resident K3 threads per SM the register budget is sized for (A/B: 1280)
+#endif
 template <int kSelThreads>
-__global__ void __launch_bounds__(kSelThreads, (kSelThreads >= 1024) ? 1 : 1280 / kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, (kSelThreads >= 1024) ? 1 : HCIR_K3_THREADS_PER_SM / kSelThreads)
 select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int ld, int64_t nq,
                       int64_t ng, int k, int64_t idx_offset, int nlists, int cap, int kc,
                       const int32_t* __restrict__ counts, const uint64_t* __restrict__ cand,
@@ -172,6 +179,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw + L.stage);
   uint64_t* sel = reinterpret_cast<uint64_t*>(smem_raw + L.sel);   // kc best by bf16 score, DESCENDING
   uint64_t* fk = reinterpret_cast<uint64_t*>(smem_raw + L.fk);     // fp32 keys of the re-scored prefix of sel
+  int32_t* clab = reinterpret_cast<int32_t*>(smem_raw + L.clab);   // class index of every re-scored candidate
   float* qrow = reinterpret_cast<float*>(smem_raw + L.qrow);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + L.hist);
   int32_t* offs = reinterpret_cast<int32_t*>(smem_raw + L.offs);
@@ -241,9 +249,10 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   int nstage = 0;
   bool staged = false;
   {
-    for_each_batch<kSelThreads>(lists, offs, nlists, cap, warp, lane, [&](const uint64_t (&kk)[kKeyBatch]) {
+    auto visit = [&](const uint64_t (&kk)[kKeyBatch]) {
       stage_batch<false>(kk, hint, stage, L.stage_cap, &scratch[9], lane);
-    });
+    };
+    for_each_batch<kSelThreads>(lists, offs, nlists, cap, warp, lane, visit);
     // the query row goes to shared memory now that the key loads have been issued
 #pragma unroll
     for (int u = 0; u < kQv; ++u) {
@@ -435,16 +444,25 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   const float dq = q_delta ? q_delta[q] : 0.0f;
   const float eps = g_delta_max * (1.0f + dq) + dq * (1.0f + 1e-6f) + eps_acc;
 
-  // fp32 re-score of sel[a..b): one row per warp while the warps suffice, else two rows per warp step
+  // fp32 re-score of sel[a..b): one row per warp while the warps suffice, else two rows per warp step.
+  // The candidates' class indices are fetched alongside (the load hides under the row gather), so the
+  // tail needs no dependent label round trip once the final ranks are known.
+  auto label_of = [&](uint32_t r) -> int32_t {
+    return (tail.labels != nullptr && static_cast<int64_t>(r) < tail.n_labels) ? __ldg(tail.labels + r) : -1;
+  };
   auto rescore = [&](int a, int b) {
     const float4* q4 = reinterpret_cast<const float4*>(qrow);
     if (b - a <= kSelWarps) {
       const int j = a + warp;
       if (j < b) {
         const uint32_t r0 = key_idx(sel[j]);
+        const int32_t l0 = (lane == 0) ? label_of(r0) : 0;
         const float s0 =
             canonical_dot(q4, reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(r0) * ld), ld4, lane);
-        if (lane == 0) fk[j] = make_key(s0, r0);
+        if (lane == 0) {
+          fk[j] = make_key(s0, r0);
+          clab[j] = l0;
+        }
       }
       return;
     }
@@ -452,12 +470,17 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       const uint32_t r0 = key_idx(sel[j]);
       const bool two = (j + 1 < b);
       const uint32_t r1 = two ? key_idx(sel[j + 1]) : r0;
+      const int32_t l0 = (lane == 0) ? label_of(r0) : 0, l1 = (lane == 0 && two) ? label_of(r1) : 0;
       float s0, s1;
       canonical_dot2(q4, reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(r0) * ld),
                      reinterpret_cast<const float4*>(g32 + static_cast<int64_t>(r1) * ld), ld4, lane, s0, s1);
       if (lane == 0) {
         fk[j] = make_key(s0, r0);
-        if (two) fk[j + 1] = make_key(s1, r1);
+        clab[j] = l0;
+        if (two) {
+          fk[j + 1] = make_key(s1, r1);
+          clab[j + 1] = l1;
+        }
       }
     }
   };
@@ -488,7 +511,10 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
 
   // ---- exact order of the re-scored set, emit top-k ---------------------------------------
   // (sel is dead from here on: its memory receives the final keys in rank order for the tail)
+  // and the stage -- dead since the rank sort -- the neighbour class indices and similarities in rank order)
   uint64_t* res = sel;
+  int32_t* lab = reinterpret_cast<int32_t*>(stage);    // [k]
+  float* rsim = reinterpret_cast<float*>(stage) + k;  // [k]   (k <= kc <= stage_cap / 8)
   for (int t = tid; t < nr; t += kSelThreads) {
     const uint64_t mine = fk[t];
     int rank = 0;
@@ -496,10 +522,21 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     if (rank < k) {
       const float s = key_sim(mine);
       res[rank] = mine;
+      rsim[rank] = s;
+      lab[rank] = clab[t];
       out_sim[q * k + rank] = s;
       out_idx[q * k + rank] = static_cast<int64_t>(key_idx(mine)) + idx_offset;
+      if (tail.out_lab) tail.out_lab[q * k + rank] = clab[t];
       if (rank == k - 1) scratch[7] = __float_as_uint(s);
     }
+  }
+  // fewer than k candidates (the query is uncertified): the missing ranks read (-inf, -1), never stale memory
+  for (int j = nr + tid; j < k; j += kSelThreads) {
+    out_sim[q * k + j] = -INFINITY;
+    out_idx[q * k + j] = -1;
+    rsim[j] = -INFINITY;
+    lab[j] = -1;
+    if (tail.out_lab) tail.out_lab[q * k + j] = -1;
   }
   __syncthreads();
   if (tid == 0) {
@@ -511,24 +548,6 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
 
   // ======================= tail: labels -> vote -> peers -> arrival =======================
   const int nres = nr < k ? nr : k;  // (< k only for uncertified queries, which are completed later)
-  // the stage is dead since the rank sort: it holds the neighbour class indices and similarities in rank order
-  int32_t* lab = reinterpret_cast<int32_t*>(stage);    // [k]
-  float* rsim = reinterpret_cast<float*>(stage) + k;  // [k]   (k <= kc <= stage_cap / 8)
-  if (tail.labels != nullptr) {
-    for (int j = tid; j < k; j += kSelThreads) {
-      int32_t l = -1;
-      float s = -INFINITY;
-      if (j < nres) {
-        const int64_t r = static_cast<int64_t>(key_idx(res[j]));
-        l = (r < tail.n_labels) ? __ldg(tail.labels + r) : -1;
-        s = key_sim(res[j]);
-      }
-      lab[j] = l;
-      rsim[j] = s;
-      if (tail.out_lab) tail.out_lab[q * k + j] = l;
-    }
-    __syncthreads();
-  }
   int64_t pred_val = 0;
   const bool do_vote = (tail.pred != nullptr) || (tail.payload == 2);
   if (do_vote && warp == 0) {

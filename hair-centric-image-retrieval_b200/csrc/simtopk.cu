@@ -16,6 +16,7 @@
 // Work item = (query tile of 128 rows) x (gallery split = contiguous range of 256-row tiles).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <utility>
 
@@ -561,7 +562,7 @@ __device__ __forceinline__ void kth2_warp_regs(const uint32_t (&rv)[8], int kA, 
 
 template <bool kBlock>
 __global__ void __launch_bounds__(kBlock ? kThrBlockThreads : kThrWarps * kWarp)
-threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int kc, int hint_rank,
+threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int kc /* = thr_rank */, int hint_rank,
                  float* __restrict__ thr0, float* __restrict__ thr_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -672,6 +673,18 @@ static int balanced_nsplit(int64_t num_qt, int64_t tiles, int64_t max_split, int
   return best;
 }
 
+// smallest j with P(Poisson(lambda) >= j) <= tail (exact summation; normal bound for large lambda)
+static int poisson_tail_rank(double lambda, double tail) {
+  if (lambda > 200.0) return static_cast<int>(lambda + 5.5 * sqrt(lambda) + 4.0);
+  double pmf = exp(-lambda), cdf = 0.0;  // P(X = 0)
+  for (int j = 1; j < 4096; ++j) {
+    cdf += pmf;                          // P(X <= j - 1)
+    if (1.0 - cdf <= tail) return j;
+    pmf *= lambda / j;
+  }
+  return 4096;
+}
+
 template <int kMode, int kCtas>
 static int launch_mode(const CUtensorMap& mq, const CUtensorMap& mg, SimParams p, int sms, cudaStream_t st) {
   p.num_qu = (p.num_qt + kCtas - 1) / kCtas;
@@ -756,7 +769,9 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     rc = launch_mode<kModeSample, 1>(mq, ms, sp, sms, st);
     if (rc != HCIR_OK) return rc;
     thr0 = reinterpret_cast<float*>(ws + plan->thr0_off);
-    HCIR_REQUIRE(plan->hint_rank >= 1 && plan->hint_rank <= plan->kc, "simtopk: bad hint_rank=%d", plan->hint_rank);
+    HCIR_REQUIRE(plan->thr_rank >= 1 && plan->thr_rank <= plan->kc && plan->hint_rank >= 1 &&
+                     plan->hint_rank <= plan->thr_rank,
+                 "simtopk: bad thr_rank=%d / hint_rank=%d (kc=%d)", plan->thr_rank, plan->hint_rank, plan->kc);
     float* thr_hi = reinterpret_cast<float*>(ws + plan->thr_hi_off);
     const bool per_block = nq <= 1024;  // few queries: a CTA per query hides the search latency
     const size_t smem = 16 + (per_block ? 2048 : 0) + static_cast<size_t>(per_block ? 1 : kThrWarps) * plan->num_chunks * 4;
@@ -765,12 +780,12 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
       HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
       threshold_kernel<true><<<static_cast<unsigned>(nq), kThrBlockThreads, smem, st>>>(
-          sp.cmax, nq, plan->num_chunks, plan->kc, plan->hint_rank, thr0, thr_hi);
+          sp.cmax, nq, plan->num_chunks, plan->thr_rank, plan->hint_rank, thr0, thr_hi);
     } else {
       HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
       threshold_kernel<false><<<static_cast<unsigned>(ceil_div_i64(nq, kThrWarps)), kThrWarps * kWarp, smem, st>>>(
-          sp.cmax, nq, plan->num_chunks, plan->kc, plan->hint_rank, thr0, thr_hi);
+          sp.cmax, nq, plan->num_chunks, plan->thr_rank, plan->hint_rank, thr0, thr_hi);
     }
     HCIR_CUDA_TRY(cudaGetLastError());
   }
@@ -816,15 +831,20 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
   plan->nsplit = pairs ? balanced_nsplit((num_qt + 1) / 2, tiles, 4 * sm_count, sm_count / 2)
                        : balanced_nsplit(num_qt, tiles, 4 * sm_count, sm_count);
 
-  // sample pass: num_chunks = 2*kc chunk maxima over S = 2*kc*chunk_w strided gallery rows, as long
-  // as the sample stays a small fraction of the gallery (its contraction is extra work)
+  // sample pass: S strided gallery rows, S chosen so that the sample holds lambda ~ 2 of the gallery's kc
+  // best rows on average (S = 2 * ng / kc, at least 1024 rows, at most 1/16 of the gallery).  The sample
+  // costs S / ng of the main pass; with the optimistic threshold below ~6.5 x kc rows pass the filter
+  // however large the gallery is, so a bigger sample buys little (C3: 16896 -> 7680 rows saves 0.08 ms
+  // of sample pass and costs 0.006 ms of longer lists).  Galleries under 64 * kc rows get no sample:
+  // everything passes (thr0 = -inf) and K3 selects from the whole row set.
   int64_t S = 0;
   int w = 0;
-  if (64ll * kc * 16 <= ng) { w = 32; S = 64ll * kc; }
-  else if (32ll * kc * 12 <= ng) { w = 16; S = 32ll * kc; }
-  else if (16ll * kc * 4 <= ng) { w = 8; S = 16ll * kc; }
-  // a big gallery affords a bigger sample (1/64 of the rows): tighter thresholds, shorter lists
-  if (w == 32 && ng / 64 > S) S = ng / 64;
+  if (64ll * kc <= ng) {
+    S = 2 * ng / kc;
+    if (S > ng / 16) S = ng / 16;
+    if (S < 1024) S = 1024;
+    w = S >= 8192 ? 32 : (S >= 2048 ? 16 : 8);
+  }
   double pass_rate = 1.0;
   if (S > 0) {
     S = (S + kBlockN - 1) / kBlockN * kBlockN;  // whole tiles
@@ -833,12 +853,26 @@ extern "C" int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_
     plan->chunk_w = w;
     plan->num_chunks = static_cast<int32_t>(S / w);
     plan->sample_nsplit = balanced_nsplit(num_qt, S / kBlockN, 4 * sm_count, sm_count);
-    // kc-th best of m chunk maxima ~ the (-m ln(1 - kc/m))-th best sample row
+    // The main-pass threshold is the r-th largest chunk maximum, r = min(kc, j):
+    //  * r = kc is the deterministic bound: kc distinct real rows score >= it, nothing below it can be a
+    //    top-kc candidate -- but ~kc*N/S rows pass it (76 x kc on the 1M-row gallery);
+    //  * r = j < kc is the OPTIMISTIC bound: the strided sample holds a Poisson(lambda = kc*S/N) number of
+    //    the gallery's kc best rows; if fewer than j of them are in the sample -- probability
+    //    1 - P(Poisson(lambda) >= j) >= 1 - 1e-7 by the choice of j -- at least kc gallery rows beat the j-th
+    //    best sample row, a fortiori the j-th largest chunk maximum.  Only ~j*N/S rows pass (4-7 x kc).
+    // Exactness never rests on that probability: K3 certifies every query against the threshold its lists
+    // really ended with, and a query whose lists came up short is completed by the second pass like any
+    // other uncertified query.  HCIR_SAFE_THR=1 (environment, measurement aid) keeps r = kc.
+    const double lambda = static_cast<double>(kc) * static_cast<double>(S) / static_cast<double>(ng);
+    const char* safe = getenv("HCIR_SAFE_THR");
+    int r = poisson_tail_rank(lambda, 1e-7);
+    if (r > kc || (safe != nullptr && safe[0] == '1')) r = kc;
+    if (r >= plan->num_chunks) r = plan->num_chunks - 1;  // (only reachable with HCIR_SAFE_THR on tiny samples)
+    plan->thr_rank = r;
+    plan->hint_rank = r;  // K3 stages every listed key (the lists are short now); see select_rescore.cu
+    // r-th best of m chunk maxima ~ the (-m ln(1 - r/m))-th best sample row
     const double m = static_cast<double>(plan->num_chunks);
-    pass_rate = -m * log(1.0 - kc / m) / static_cast<double>(S);
-    // staging hint for K3: the j-th best sample row, j such that ~4*kc gallery rows beat it
-    int64_t j = (4ll * kc * S + ng - 1) / ng;
-    plan->hint_rank = static_cast<int32_t>(j < 1 ? 1 : (j > kc ? kc : j));
+    pass_rate = -m * log(1.0 - r / m) / static_cast<double>(S);
   }
   // list capacity: expected appends per (query, split) list with head-room, bounded so that the
   // prune path (not the workspace) absorbs adversarial data

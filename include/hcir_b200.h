@@ -78,10 +78,13 @@ int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, float* out_f
  *   1. sample pass   the same contraction over a strided sample of `sample_rows` gallery rows
  *                    (addressed in place through the TMA row stride); the epilogue keeps only
  *                    the maximum of every `chunk_w` consecutive sample columns;
- *   2. thresholds    thr0[q] = kc-th largest chunk maximum: >= kc real gallery rows score
- *                    >= thr0[q], so nothing <= thr0[q] can be a top-kc candidate; thr_hi[q] =
- *                    a higher order statistic that ~4*kc gallery rows are expected to beat
- *                    (a staging hint for hcir_select_rescore, verified there);
+ *   2. thresholds    thr0[q] = thr_rank-th largest chunk maximum, thr_rank = min(kc, j):
+ *                    kc is the deterministic bound (kc real gallery rows score >= it); j is the
+ *                    Poisson-tail rank for which, with probability >= 1 - 1e-7 per query, at least
+ *                    kc gallery rows still beat the statistic while only ~4-7 x kc rows pass it.
+ *                    Exactness never depends on that probability: hcir_select_rescore certifies
+ *                    against the threshold the lists really ended with; a short query is completed
+ *                    like any other uncertified one.  thr_hi[q] = staging hint for K3 (= thr0 now);
  *   3. main pass     full contraction; the epilogue compares every accumulator value with the
  *                    query's threshold and appends the survivors (64-bit keys) to one list per
  *                    (query, gallery split).  A list that fills up is pruned back to its kc
@@ -105,10 +108,13 @@ typedef struct {
   int32_t num_chunks;    /* sample_rows / chunk_w                                          */
   int32_t sample_nsplit; /* splits of the sample pass                                      */
   int32_t nlists;        /* candidate lists per query (= nsplit x column slices per tile)    */
-  int32_t hint_rank;     /* thr_hi[q] = hint_rank-th largest chunk maximum (K3 staging hint) */
+  int32_t hint_rank;     /* thr_hi[q] = hint_rank-th largest chunk maximum (K3 staging hint; <= thr_rank) */
   int32_t q_rows;        /* rows the query buffer really holds (>= nq; 0 = nq).  A buffer padded
                           * to a multiple of 128 rows keeps the query TMA box in bounds, which
                           * is measurably faster than TMA out-of-bounds zero fill for small nq */
+  int32_t thr_rank;      /* thr0[q] = thr_rank-th largest chunk maximum = the main-pass threshold:
+                          * kc (deterministic bound) or the smaller Poisson-tail rank (simtopk.cu)  */
+  int32_t reserved_;
   uint64_t counts_off, thr_out_off, thr0_off, thr_hi_off, cmax_off, keys_off;
   uint64_t bytes;        /* total workspace bytes                                          */
 } hcir_plan_t;

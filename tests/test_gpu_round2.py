@@ -450,14 +450,21 @@ def test_kth_neighbour_euclidean_branch_and_metrics_on_device():
     from hcir_b200 import metrics
     g = torch.Generator().manual_seed(18)
     emb = torch.randn(256, 512, generator=g) * (1.0 + torch.rand(256, 1, generator=g))   # unequal norms
-    dist = torch.cdist(emb, emb)
-    _, order = torch.sort(-dist, dim=1, descending=True)
+    dist = torch.cdist(emb, emb)                                   # the reference's call (fp32, mm-based:
+    _, order = torch.sort(-dist, dim=1, descending=True)           #   abs error up to ~0.05 at these norms)
+    d64 = torch.cdist(emb.double(), emb.double(), compute_mode="donot_use_mm_for_euclid_dist")
+    _, o64 = torch.sort(d64, dim=1)
     for k in (1, 7, 64):
         ours = metrics.kth_neighbour(emb, k, metric="euclidean")
+        # exact ranking (fp64 distances) except true near-ties
+        for r in torch.nonzero(ours != o64[:, k - 1]).flatten().tolist():
+            assert abs(float(d64[r, ours[r]] - d64[r, o64[r, k - 1]])) < 1e-5 * float(d64[r, ours[r]])
+        assert (ours == o64[:, k - 1]).float().mean() > 0.99
+        # the reference's fp32 cdist ranking agrees wherever its own rounding error cannot flip the order
         ref = order[:, k - 1]
-        for r in torch.nonzero(ours != ref).flatten().tolist():      # only near-ties of the reference's own distances
-            assert abs(float(dist[r, ours[r]] - dist[r, ref[r]])) < 1e-4 * float(dist[r, ref[r]]) + 1e-5
-        assert (ours == ref).float().mean() > 0.98
+        for r in torch.nonzero(ours != ref).flatten().tolist():
+            assert abs(float(d64[r, ours[r]] - d64[r, ref[r]])) < 0.06
+        assert (ours == ref).float().mean() > 0.97
     assert torch.equal(metrics.kth_neighbour(emb.cuda(), 1, metric="euclidean").cpu(), torch.arange(256))
     with pytest.raises(ValueError):
         metrics.kth_neighbour(emb, 3, metric="manhattan")
