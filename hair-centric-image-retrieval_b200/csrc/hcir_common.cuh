@@ -102,9 +102,10 @@ __device__ __forceinline__ float canonical_dot(const float4* __restrict__ q4,
 // Two rows at once (same per-row arithmetic order as canonical_dot, so bit-identical results).  The row
 // gathers of the re-score are latency-bound: the loads of kDotGroup consecutive chunks of BOTH rows
 // (2 * kDotGroup independent 16-byte loads per lane) are issued before any is consumed, so a warp keeps
-// 3 KiB in flight instead of whatever the compiler's unrolling happens to stagger.
+// 4 KiB in flight instead of whatever the compiler's unrolling happens to stagger (A/B on the GPU box,
+// profiles/README.md r2d: groups of 2 / 3 / 4 chunks -> K3 on the C5 shard 9.9 / 9.2 / 8.7 ms).
 #ifndef HCIR_DOT_GROUP
-#define HCIR_DOT_GROUP 3
+#define HCIR_DOT_GROUP 4
 #endif
 constexpr int kDotGroup = HCIR_DOT_GROUP;
 __device__ __forceinline__ void canonical_dot2(const float4* __restrict__ q4, const float4* __restrict__ ga,

@@ -36,7 +36,7 @@ static SelSmem sel_smem_layout(int nlists, int kc, int ld) {
   L.stage = o; o += static_cast<size_t>(L.stage_cap) * 8;
   L.sel = o; o += static_cast<size_t>(kc) * 8;
   L.fk = o; o += static_cast<size_t>(kc) * 8;
-  L.clab = o; o += static_cast<size_t>(kc) * 4;
+  L.clab = o; o += (static_cast<size_t>(kc) * 4 + 15) / 16 * 16;  // keeps qrow (float4 accesses) 16-byte aligned
   L.qrow = o; o += static_cast<size_t>(ld) * 4;
   L.hist = o; o += kBins * 4;
   L.offs = o; o += (static_cast<size_t>(nlists) + 1) * 4;
