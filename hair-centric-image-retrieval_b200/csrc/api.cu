@@ -1,6 +1,7 @@
 // Error plumbing and device checks for the hcir_b200 C ABI (include/hcir_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "hcir_common.cuh"
 
@@ -18,6 +19,14 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
   return HCIR_ECUDA;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("HCIR_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int check_device() {

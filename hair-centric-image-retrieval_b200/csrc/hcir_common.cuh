@@ -41,6 +41,33 @@ int check_device();  // HCIR_OK iff current device is sm_100
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// ---- programmatic dependent launch ---------------------------------------------------------
+// The kernels of a search step are launched with the programmatic-stream-serialization attribute and
+// call pdl_wait() (griddepcontrol.wait: returns once the preceding kernel of the stream has completed
+// and its writes are visible) before they touch anything a predecessor produced.  The dependent grid's
+// launch latency and prologue (barrier init, TMEM allocation, tensor-map prefetch) then overlap the
+// predecessor's tail instead of following its completion -- the step is a chain of 5-6 short kernels
+// in one CUDA graph, so the node-to-node gaps are a measurable part of the streaming-regime step.
+// Without the launch attribute the instruction is a no-op.  HCIR_PDL=0 (environment) turns it off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();  // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- peer region header (peer.cu; K3's tail and the fused wait+merge+vote kernel write / poll it) ----
 //   int64 words: [0..15] arrivals[r]  steps whose block from rank r has landed here (monotone)
 //                [16..31] meta[0][r], [32..47] meta[1][r]  one word per rank and parity (uncertified count)

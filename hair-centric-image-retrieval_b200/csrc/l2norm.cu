@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(kNormWarpsPerBlock* kWarp)
 l2norm_cast_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ld,
                    float* __restrict__ out_delta, bool vec_ok) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kNormWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * kNormWarpsPerBlock;
@@ -99,8 +100,8 @@ extern "C" int hcir_l2norm_cast(const float* x, int64_t n, int d, int64_t ldx, f
   const int64_t want = ceil_div_i64(n, kNormWarpsPerBlock);
   const int64_t cap = static_cast<int64_t>(sms) * 16;  // 16 resident CTAs of 8 warps per SM, grid-stride
   const int grid = static_cast<int>(want < cap ? want : cap);
-  l2norm_cast_kernel<<<grid, kNormWarpsPerBlock * kWarp, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, n, d, ldx, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld, out_delta, vec_ok);
-  HCIR_CUDA_TRY(cudaGetLastError());
+  HCIR_CUDA_TRY(launch_pdl(l2norm_cast_kernel, dim3(grid), dim3(kNormWarpsPerBlock * kWarp), 0,
+                           static_cast<cudaStream_t>(stream), x, n, d, ldx, out_f32,
+                           reinterpret_cast<__nv_bfloat16*>(out_bf16), ld, out_delta, vec_ok));
   return HCIR_OK;
 }

@@ -35,6 +35,7 @@ merge_topk_kernel(const char* __restrict__ gsim, const char* __restrict__ gidx, 
                   float* __restrict__ out_sim, int64_t* __restrict__ out_idx, int32_t* __restrict__ out_lab,
                   size_t parity_stride, const MergeTail mt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();
   int64_t st = 0;
   if (mt.hdr != nullptr) {  // peer exchange: this step's blocks live in parity (st & 1) once every rank arrived
     st = *mt.step + 1;
@@ -135,10 +136,10 @@ static int merge_launch(const void* gsim, const void* gidx, const void* glab, si
   HCIR_REQUIRE(mt.pred == nullptr || (glab != nullptr && mt.num_classes > 0), "merge_topk: a vote needs labels");
   HCIR_CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-  merge_topk_kernel<<<static_cast<unsigned>(nq), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const char*>(gsim), static_cast<const char*>(gidx), static_cast<const char*>(glab), stride_sim,
-      stride_idx, stride_lab, G, nq, k, out_sim, out_idx, out_lab, parity_stride, mt);
-  HCIR_CUDA_TRY(cudaGetLastError());
+  HCIR_CUDA_TRY(launch_pdl(merge_topk_kernel, dim3(static_cast<unsigned>(nq)), dim3(128), smem,
+                           static_cast<cudaStream_t>(stream), static_cast<const char*>(gsim),
+                           static_cast<const char*>(gidx), static_cast<const char*>(glab), stride_sim, stride_idx,
+                           stride_lab, G, nq, k, out_sim, out_idx, out_lab, parity_stride, mt));
   return HCIR_OK;
 }
 

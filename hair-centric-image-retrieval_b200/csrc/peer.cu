@@ -66,6 +66,7 @@ peer_push_kernel(const uint4* __restrict__ src, size_t n16, PeerPtrs peers, int 
 
 __global__ void __launch_bounds__(32)
 peer_wait_kernel(int64_t* __restrict__ hdr, int world, int64_t* __restrict__ step, int64_t timeout_ns) {
+  pdl_wait();
   const int64_t st = *step + 1;
   const bool all_ok = peer_wait_arrivals(hdr, world, st, timeout_ns, threadIdx.x);
   if (threadIdx.x == 0) {
@@ -162,8 +163,7 @@ extern "C" int hcir_peer_wait(void* region_local, int world, int64_t* step, int6
   using namespace hcir;
   HCIR_REQUIRE(region_local != nullptr && step != nullptr && world >= 1 && world <= kPeerMax,
                "peer_wait: bad arguments");
-  peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<int64_t*>(region_local), world, step,
-                                                                    timeout_ns);
-  HCIR_CUDA_TRY(cudaGetLastError());
+  HCIR_CUDA_TRY(launch_pdl(peer_wait_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream),
+                           static_cast<int64_t*>(region_local), world, step, timeout_ns));
   return HCIR_OK;
 }

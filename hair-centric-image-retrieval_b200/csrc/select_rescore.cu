@@ -189,6 +189,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   const int64_t q = blockIdx.x;
   const int ld4 = ld >> 2;
   const uint64_t* lists = cand + q * nlists * static_cast<int64_t>(cap);
+  pdl_wait();
 
   // ---- start: issue the query-row loads (consumed after the key pass); every warp fetches the
   // lengths / thresholds of ITS lists (w, w+W, ...) and goes straight to reading keys -- there is
@@ -663,9 +664,10 @@ static int launch_select(const float* q_f32, const float* g_f32, int ld, int64_t
   do {                                                                                                             \
     HCIR_CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                        static_cast<int>(L.total)));                                                \
-    select_rescore_kernel<T_><<<static_cast<unsigned>(nq), T_, L.total, st>>>(                                     \
-        q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts, cand, thr_out, thr_hi, \
-        q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list, state, L, tp);                               \
+    HCIR_CUDA_TRY(launch_pdl(select_rescore_kernel<T_>, dim3(static_cast<unsigned>(nq)), dim3(T_), L.total, st,    \
+                             q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts,   \
+                             cand, thr_out, thr_hi, q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list,  \
+                             state, L, tp));                                                                       \
   } while (0)
   // CTA width: forced by the plan flags (measurement aid) or chosen from the shape
   const int width = (plan->flags & HCIR_FLAG_K3_WIDTH_MASK) >> HCIR_FLAG_K3_WIDTH_SHIFT;

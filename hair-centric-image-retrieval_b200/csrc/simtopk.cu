@@ -183,6 +183,9 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if constexpr (kCtas == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is independent of the preceding kernel (its CTA has left this SM, or this CTA
+  // could not have been placed: 214 KiB of shared memory); the operands, thresholds and lists are not
+  pdl_wait();
 
   if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
@@ -565,6 +568,7 @@ __global__ void __launch_bounds__(kBlock ? kThrBlockThreads : kThrWarps * kWarp)
 threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int kc /* = thr_rank */, int hint_rank,
                  float* __restrict__ thr0, float* __restrict__ thr_hi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = kBlock ? static_cast<int64_t>(blockIdx.x) : static_cast<int64_t>(blockIdx.x) * kThrWarps + warp;
   if (q >= nq) return;  // warp-uniform (block-uniform for kBlock)
@@ -699,13 +703,15 @@ static int launch_mode(const CUtensorMap& mq, const CUtensorMap& mg, SimParams p
   cfg.blockDim = dim3(kSimThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (pdl_enabled() && kCtas == 1) ? 2 : 1;
   HCIR_CUDA_TRY(cudaLaunchKernelEx(&cfg, simtopk_kernel<kMode, kCtas>, mq, mg, p));
   return HCIR_OK;
 }
@@ -779,13 +785,14 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
     if (per_block) {
       HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-      threshold_kernel<true><<<static_cast<unsigned>(nq), kThrBlockThreads, smem, st>>>(
-          sp.cmax, nq, plan->num_chunks, plan->thr_rank, plan->hint_rank, thr0, thr_hi);
+      HCIR_CUDA_TRY(launch_pdl(threshold_kernel<true>, dim3(static_cast<unsigned>(nq)), dim3(kThrBlockThreads), smem, st,
+                               sp.cmax, nq, plan->num_chunks, plan->thr_rank, plan->hint_rank, thr0, thr_hi));
     } else {
       HCIR_CUDA_TRY(cudaFuncSetAttribute(threshold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-      threshold_kernel<false><<<static_cast<unsigned>(ceil_div_i64(nq, kThrWarps)), kThrWarps * kWarp, smem, st>>>(
-          sp.cmax, nq, plan->num_chunks, plan->thr_rank, plan->hint_rank, thr0, thr_hi);
+      HCIR_CUDA_TRY(launch_pdl(threshold_kernel<false>, dim3(static_cast<unsigned>(ceil_div_i64(nq, kThrWarps))),
+                               dim3(kThrWarps * kWarp), smem, st, sp.cmax, nq, plan->num_chunks, plan->thr_rank,
+                               plan->hint_rank, thr0, thr_hi));
     }
     HCIR_CUDA_TRY(cudaGetLastError());
   }

@@ -756,13 +756,20 @@ class SearchSession:
         if self.out_lab is not None:
             self._gather_packed_labels()
 
-    def submit(self, queries) -> PendingStep:
+    @property
+    def input(self) -> torch.Tensor:
+        """The step's static input buffer [nq, d] fp32 on the device.  A producer that writes its queries
+        straight into it (the encoder's output, an H2D copy) calls ``run()`` / ``submit()`` without an
+        argument and saves the device-to-device copy in front of every replay."""
+        return self.q_in
+
+    def submit(self, queries=None) -> PendingStep:
         """Pipelined ``run``: enqueue the step and return at once.  ``result()`` of the returned
         handle gives (pred | None, sims, idx) as fresh device tensors; uncertified queries (rare) are
         completed there by re-running this batch through the eager path.  ``queries`` must stay
         unmodified until then.  At most 8 steps may be pending per session."""
         b = self.bank
-        if tuple(queries.shape) != (self.nq, b.d):
+        if queries is not None and tuple(queries.shape) != (self.nq, b.d):
             raise ValueError(f"session was built for queries of shape {(self.nq, b.d)}, got {tuple(queries.shape)}")
         with torch.cuda.device(b.device):
             ring = self.__dict__.get("_flag_ring")
@@ -771,7 +778,10 @@ class SearchSession:
                 self._submitted = 0
             slot = ring[self._submitted % 8]
             self._submitted += 1
-            self.q_in.copy_(queries, non_blocking=True)
+            if queries is not None:
+                self.q_in.copy_(queries, non_blocking=True)
+            else:
+                queries = self.q_in.clone()   # the redo path needs the batch after q_in has been overwritten
             self.graph.replay()
             b.launches += self.kernels_per_run
             res = (self.pred.clone() if self.pred is not None else None, self.out_sim.clone(), self.out_idx.clone())
@@ -789,16 +799,18 @@ class SearchSession:
 
         return PendingStep(ev, slot, lambda f: int(f[0]) > 0, res, redo)
 
-    def run(self, queries, check: bool = True):
-        """queries: [nq, d] fp32 tensor (device, or host -- pinned for an async copy).  Returns
+    def run(self, queries=None, check: bool = True):
+        """queries: [nq, d] fp32 tensor (device, or host -- pinned for an async copy), or None when the
+        caller has filled ``self.input`` itself.  Returns
         (pred [nq] int64 | None, sims [nq, k], idx [nq, k]) as DEVICE tensors owned by the session
         (valid until the next run).  ``check=False``: only replay; the caller reads the uncertified
         count (multi-GPU: from the gathered trailers) and calls ``finish_uncertified``."""
         b = self.bank
-        if tuple(queries.shape) != (self.nq, b.d):
+        if queries is not None and tuple(queries.shape) != (self.nq, b.d):
             raise ValueError(f"session was built for queries of shape {(self.nq, b.d)}, got {tuple(queries.shape)}")
         with torch.cuda.device(b.device):
-            self.q_in.copy_(queries, non_blocking=True)
+            if queries is not None:
+                self.q_in.copy_(queries, non_blocking=True)
             self.graph.replay()
             b.launches += self.kernels_per_run
             if not check:

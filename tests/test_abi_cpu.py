@@ -46,6 +46,12 @@ def test_sass_is_blackwell_native():
     assert "HGMMA" not in sass
 
 
+def _poisson_tail(lam, j):
+    """P(Poisson(lam) >= j)"""
+    import math
+    return 1.0 - sum(math.exp(-lam) * lam ** i / math.factorial(i) for i in range(j))
+
+
 def test_plan_is_consistent():
     lib = _lib.load()
     p = _lib.Plan()
@@ -62,9 +68,13 @@ def test_plan_is_consistent():
         assert p.keys_off % 256 == 0 and p.cmax_off % 256 == 0
         if p.sample_rows:
             assert p.sample_rows % 256 == 0 and p.chunk_w in (8, 16, 32)
-            assert p.num_chunks * p.chunk_w == p.sample_rows and p.num_chunks >= 2 * p.kc
+            assert p.num_chunks * p.chunk_w == p.sample_rows
             assert (p.sample_rows - 1) * p.sample_stride < ng and p.sample_rows * 4 <= ng + 1024
-            assert 1 <= p.hint_rank <= p.kc
+            # the main-pass threshold is the thr_rank-th largest chunk maximum: never looser than the
+            # deterministic kc-th, never more than the chunks there are; the sample holds ~2 of the top-kc rows
+            assert 1 <= p.hint_rank <= p.thr_rank <= min(p.kc, p.num_chunks - 1)
+            lam = p.kc * p.sample_rows / ng
+            assert p.thr_rank == p.kc or (lam <= 20 and _poisson_tail(lam, p.thr_rank) <= 1e-7 < _poisson_tail(lam, p.thr_rank - 1))
             st = -(-(p.sample_rows // 256) // p.sample_nsplit)
             assert -(-(p.sample_rows // 256) // st) == p.sample_nsplit
         else:
