@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/hcir_b200.h"
 
@@ -40,6 +41,27 @@ int check_device();  // HCIR_OK iff current device is sm_100
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// ---- device-side bounds checks (debug build) ---------------------------------------------
+// compute-sanitizer is closed on the GPU pool this was developed on, so the indices the sanitizer would
+// have watched -- list appends of the K2 epilogue, the shared-memory stages / histograms / rank arrays of
+// K3, the merge ranks of K5 -- carry explicit checks that a build with -DHCIR_BOUNDS_CHECK
+// (HCIR_NVCC_EXTRA="-DHCIR_BOUNDS_CHECK") turns into printf + trap.  The whole -m gpu suite runs clean
+// under that build (profiles/README.md); production builds compile the checks away.
+#ifdef HCIR_BOUNDS_CHECK
+#define HCIR_DEV_CHECK(cond)                                                                              \
+  do {                                                                                                    \
+    if (!(cond)) {                                                                                        \
+      printf("HCIR bounds check failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__,   \
+             static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));                                \
+      __trap();                                                                                           \
+    }                                                                                                     \
+  } while (0)
+#else
+#define HCIR_DEV_CHECK(cond) \
+  do {                       \
+  } while (0)
+#endif
 
 // ---- programmatic dependent launch ---------------------------------------------------------
 // The kernels of a search step are launched with the programmatic-stream-serialization attribute and

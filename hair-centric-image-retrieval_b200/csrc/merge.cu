@@ -82,6 +82,7 @@ merge_topk_kernel(const char* __restrict__ gsim, const char* __restrict__ gidx, 
       }
       rank += lo;
     }
+    HCIR_DEV_CHECK(rank >= 0 && rank < total);
     if (rank < k) {
       const int g = i / k, j = i - g * k;
       const int64_t src = q * k + j;

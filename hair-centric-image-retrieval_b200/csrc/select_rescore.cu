@@ -129,6 +129,7 @@ __device__ __forceinline__ void stage_batch(const uint64_t (&kk)[kKeyBatch], uin
     if (hits & (1u << u)) {
       if (at < static_cast<uint32_t>(stage_cap)) stage[at] = raw2key(kk[u]);
       ++at;
+      HCIR_DEV_CHECK(key_idx(raw2key(kk[u])) < 0x7FFFFFFFu);   // a listed key names a real gallery row
     }
   }
 }
@@ -297,8 +298,12 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
         for (int u = 0; u < kKeyBatch; ++u) {
           if (kk[u] == 0ull) continue;
           const uint32_t o = f2ord(__uint_as_float(static_cast<uint32_t>(kk[u] >> 32)));
-          if (o >= lo && o <= hi) atomicAdd(&hist[(o - lo) >> shift], 1u);
-          else if (check_range) scratch[13] = 1u;
+          if (o >= lo && o <= hi) {
+            HCIR_DEV_CHECK(((o - lo) >> shift) < static_cast<uint32_t>(kBins));
+            atomicAdd(&hist[(o - lo) >> shift], 1u);
+          } else if (check_range) {
+            scratch[13] = 1u;
+          }
         }
       });
       __syncthreads();
@@ -387,8 +392,10 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     const uint32_t lo = scratch[15], span = scratch[16] - lo;
     int shift = 0;
     while ((span >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
-    for (int i = tid; i < nstage; i += kSelThreads)
+    for (int i = tid; i < nstage; i += kSelThreads) {
+      HCIR_DEV_CHECK(((static_cast<uint32_t>(stage[i] >> 32) - lo) >> shift) < static_cast<uint32_t>(kBins));
       atomicAdd(&hist[(static_cast<uint32_t>(stage[i] >> 32) - lo) >> shift], 1u);
+    }
     __syncthreads();
     if (warp == 0) {  // bin that holds the kc-th best, scanning from the top
       constexpr int per = kBins / kWarp;
@@ -429,6 +436,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
         uint32_t base = 0u;
         if (lane == 0) base = atomicAdd(&scratch[17], static_cast<uint32_t>(__popc(b)));
         base = __shfl_sync(kFull, base, 0);
+        HCIR_DEV_CHECK(!hit || base + __popc(b & ((1u << lane) - 1u)) < static_cast<uint32_t>(kCompactCap));
         if (hit) compact[base + __popc(b & ((1u << lane) - 1u))] = key;
       }
       __syncthreads();
@@ -509,6 +517,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   }
   __syncthreads();
   const int nr = n1 + static_cast<int>(scratch[6]);
+  HCIR_DEV_CHECK(nr <= ncand && ncand <= kc && nstage <= L.stage_cap && 8 * k <= 8 * L.stage_cap);
   rescore(n1, nr);
   __syncthreads();
 
@@ -546,7 +555,11 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
     const float sk = (nr >= k) ? __uint_as_float(scratch[7]) : -INFINITY;
     // rows outside `sel` score <= tprime in bf16 (list thresholds, kc cut), hence <= tprime + eps in fp32
     const bool certified = (nr >= k) && (tprime + eps < sk);
-    if (!certified) uncert_list[atomicAdd(&state[0], 1)] = static_cast<int32_t>(q);
+    if (!certified) {
+      const int at = atomicAdd(&state[0], 1);
+      HCIR_DEV_CHECK(at >= 0 && at < nq);
+      uncert_list[at] = static_cast<int32_t>(q);
+    }
   }
 
   // ======================= tail: labels -> vote -> peers -> arrival =======================

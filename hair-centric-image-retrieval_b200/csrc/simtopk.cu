@@ -381,6 +381,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
               const int lim = rem >= 32 ? 32 : (rem > 0 ? static_cast<int>(rem) : 0);
               scan_chunk<true>(v, thr, buf, cnt, gcol0, lim, stage_lane);
             }
+            HCIR_DEV_CHECK(cnt >= 0 && cnt <= p.cap);   // the append stayed inside this list
             if (kDump && active) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -401,6 +402,7 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 cnt = p.kc;
                 thr = key_sim(tk);
               }
+              HCIR_DEV_CHECK(bcnt > p.kc && bcnt <= p.cap);
             }
           }
         }
