@@ -532,37 +532,58 @@ __device__ __forceinline__ void kth2_block(const uint32_t* vals, int n, int kA, 
   outB = prefB;
 }
 
-// One warp, at most 256 values held in REGISTERS (8 per lane; 0 = padding, below every candidate):
-// the kA-th and kB-th largest by one joint bitwise binary search -- per step 2 x 8 compares and two
-// independent warp reductions, no shared-memory traffic.
-__device__ __forceinline__ void kth2_warp_regs(const uint32_t (&rv)[8], int kA, int kB, uint32_t& outA,
+// One warp, at most 32 * kRegs values held in REGISTERS (kRegs per lane; 0 = padding, below every
+// candidate): the kA-th and kB-th largest by one joint bitwise binary search -- per step 2 x kRegs compares
+// and two independent warp reductions, no shared-memory traffic.  kA == kB (the optimistic threshold: one
+// statistic serves as main-pass threshold and staging hint) runs a single search.
+template <int kRegs>
+__device__ __forceinline__ void kth2_warp_regs(const uint32_t (&rv)[kRegs], int kA, int kB, uint32_t& outA,
                                                uint32_t& outB) {
   uint32_t diff = 0u;
   const uint32_t v0 = __shfl_sync(kFull, rv[0], 0);  // lane 0, slot 0 is always a real value
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < kRegs; ++i)
     if (rv[i] != 0u) diff |= rv[i] ^ v0;
   diff = __reduce_or_sync(kFull, diff);
   outA = outB = v0;
   if (diff == 0u) return;
   const int hb = 31 - __clz(diff);
   uint32_t pa = (hb == 31) ? 0u : (v0 & ~((2u << hb) - 1u)), pb = pa;
+  const bool same = (kA == kB);
 #pragma unroll 1
   for (int bit = hb; bit >= 0; --bit) {
     const uint32_t ca = pa | (1u << bit), cb = pb | (1u << bit);
     int na = 0, nb = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kRegs; ++i) {
       na += (rv[i] >= ca) ? 1 : 0;
-      nb += (rv[i] >= cb) ? 1 : 0;
+      if (!same) nb += (rv[i] >= cb) ? 1 : 0;
     }
     na = __reduce_add_sync(kFull, na);
-    nb = __reduce_add_sync(kFull, nb);
+    if (!same) nb = __reduce_add_sync(kFull, nb);
     if (na >= kA) pa = ca;
-    if (nb >= kB) pb = cb;
+    if (same) pb = pa;
+    else if (nb >= kB) pb = cb;
   }
   outA = pa;
   outB = pb;
+}
+
+template <int kRegs>
+__device__ __forceinline__ void threshold_in_registers(const float* __restrict__ src, int num_chunks, int kc,
+                                                       int hint_rank, int lane, float* thr0, float* thr_hi) {
+  uint32_t rv[kRegs];
+#pragma unroll
+  for (int i = 0; i < kRegs; ++i) {
+    const int c = lane + i * kWarp;
+    rv[i] = (c < num_chunks) ? max(f2ord(src[c]), 1u) : 0u;  // real values are never 0 (= padding)
+  }
+  uint32_t a, b;
+  kth2_warp_regs<kRegs>(rv, kc, hint_rank, a, b);
+  if (lane == 0) {
+    *thr0 = ord2f(a);
+    *thr_hi = ord2f(b);
+  }
 }
 
 template <bool kBlock>
@@ -579,19 +600,10 @@ threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int
   uint32_t* vals = red + 4 + (kBlock ? 512 : static_cast<size_t>(warp) * num_chunks);
   const float* src = cmax + q * static_cast<int64_t>(num_chunks);
   const int tid = kBlock ? threadIdx.x : lane, nthr = kBlock ? kThrBlockThreads : kWarp;
-  if (!kBlock && num_chunks <= 256 && num_chunks >= kc) {  // warp-uniform: the whole search in registers
-    uint32_t rv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = lane + i * kWarp;
-      rv[i] = (c < num_chunks) ? max(f2ord(src[c]), 1u) : 0u;  // real values are never 0 (= padding)
-    }
-    uint32_t a, b;
-    kth2_warp_regs(rv, kc, hint_rank, a, b);
-    if (lane == 0) {
-      thr0[q] = ord2f(a);
-      thr_hi[q] = ord2f(b);
-    }
+  if (!kBlock && num_chunks <= 1024 && num_chunks >= kc) {  // warp-uniform: the whole search in registers
+    if (num_chunks <= 256) threshold_in_registers<8>(src, num_chunks, kc, hint_rank, lane, thr0 + q, thr_hi + q);
+    else if (num_chunks <= 512) threshold_in_registers<16>(src, num_chunks, kc, hint_rank, lane, thr0 + q, thr_hi + q);
+    else threshold_in_registers<32>(src, num_chunks, kc, hint_rank, lane, thr0 + q, thr_hi + q);
     return;
   }
   for (int i = tid; i < num_chunks; i += nthr) vals[i] = f2ord(src[i]);
@@ -605,7 +617,7 @@ threshold_kernel(const float* __restrict__ cmax, int64_t nq, int num_chunks, int
       h = ord2f(b);
     } else {
       t = ord2f(kth_u32<false>(vals, num_chunks, kc, red));
-      h = ord2f(kth_u32<false>(vals, num_chunks, hint_rank, red));
+      h = (hint_rank == kc) ? t : ord2f(kth_u32<false>(vals, num_chunks, hint_rank, red));
     }
   }
   if (tid == 0) {
