@@ -22,6 +22,10 @@
 namespace hcir {
 
 constexpr int kRound1Slack = 6;
+#ifndef HCIR_K3_PREFETCH_AHEAD
+#define HCIR_K3_PREFETCH_AHEAD 0
+#endif
+constexpr int kPrefetchAhead = HCIR_K3_PREFETCH_AHEAD;  // gather steps whose rows are prefetched into L2 (0 = off, the default)
 constexpr int kBins = 2048;  // histogram bins of the fallback streaming selection
 
 struct SelSmem {  // offsets (bytes) into dynamic shared memory
@@ -477,7 +481,25 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       }
       return;
     }
-    for (int j = a + 2 * warp; j < b; j += 2 * kSelWarps) {
+    // EXPERIMENT, off by default (-DHCIR_K3_PREFETCH_AHEAD=n): request the rows of the step n steps ahead into
+    // L2 with prefetch instructions (no registers, no scoreboard) so that later steps hit L2.  Measured (r2k):
+    // it makes K3 SLOWER -- C3 0.45 -> 0.52 / 0.57 / 0.58 ms for n = 2 / 4 / 8, C5 shard 8.9 -> 13.7 ms -- i.e.
+    // the row gathers are not short of requests in flight; ~4.3 TB/s is what random 3-8 KB rows get here.
+    const int stride = 2 * kSelWarps;
+    const int lines = ld4 >> 3;  // 128-byte lines per row
+    auto prefetch_pair = [&](int jp) {
+      if (jp >= b) return;
+      const char* p0 = reinterpret_cast<const char*>(g32 + static_cast<int64_t>(key_idx(sel[jp])) * ld);
+      for (int l = lane; l < lines; l += kWarp) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + l * 128));
+      if (jp + 1 < b) {
+        const char* p1 = reinterpret_cast<const char*>(g32 + static_cast<int64_t>(key_idx(sel[jp + 1])) * ld);
+        for (int l = lane; l < lines; l += kWarp) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + l * 128));
+      }
+    };
+#pragma unroll
+    for (int sft = 1; sft < kPrefetchAhead; ++sft) prefetch_pair(a + 2 * warp + sft * stride);
+    for (int j = a + 2 * warp; j < b; j += stride) {
+      if constexpr (kPrefetchAhead > 0) prefetch_pair(j + kPrefetchAhead * stride);
       const uint32_t r0 = key_idx(sel[j]);
       const bool two = (j + 1 < b);
       const uint32_t r1 = two ? key_idx(sel[j + 1]) : r0;
