@@ -33,7 +33,9 @@ class Tail(C.Structure):
     _fields_ = [("labels", C.c_void_p), ("n_labels", C.c_int64), ("num_classes", C.c_int32), ("T", C.c_float),
                 ("classes", C.c_void_p), ("pred", C.c_void_p), ("out_lab", C.c_void_p),
                 ("world", C.c_int32), ("rank", C.c_int32), ("payload", C.c_int32), ("reserved_", C.c_int32),
-                ("slot_bytes", C.c_uint64), ("regions", C.c_void_p * 16), ("step", C.c_void_p)]
+                ("slot_bytes", C.c_uint64), ("regions", C.c_void_p * 16), ("step", C.c_void_p),
+                ("qmap", C.c_void_p), ("active", C.c_void_p), ("commit_certified_only", C.c_int32),
+                ("no_signal", C.c_int32), ("out_rows", C.c_int64)]
 
 
 PAYLOAD_BLOCK, PAYLOAD_PRED = 1, 2
@@ -52,6 +54,9 @@ SIGNATURES = {
     "hcir_l2norm_cast": (_INT, [_P, _I64, _INT, _I64, _P, _P, _INT, _P, _P]),
     "hcir_simtopk_plan": (_INT, [_I64, _I64, _INT, _INT, _INT, C.POINTER(Plan)]),
     "hcir_simtopk": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P]),
+    "hcir_simtopk_gated": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P, _P]),
+    "hcir_retry_setup": (_INT, [_P, _P, _P, _INT, _I64, _INT, _P, _P, _P, _F, _F, _INT, _P, _P, _P, _P, _P, _P, _P,
+                                _P, _P, _P]),
     "hcir_simtopk_debug": (_INT, [_P, _I64, _P, _I64, _INT, C.POINTER(Plan), _P, _P, _P]),
     "hcir_select_rescore": (_INT, [_P, _P, _INT, _I64, _I64, _INT, _I64, C.POINTER(Plan), _P, _P, _F, _F,
                                    _P, _P, _P, _P, C.POINTER(Tail), _P]),

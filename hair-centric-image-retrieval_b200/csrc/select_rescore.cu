@@ -35,7 +35,19 @@ struct SelSmem {  // offsets (bytes) into dynamic shared memory
 
 static SelSmem sel_smem_layout(int nlists, int kc, int ld) {
   SelSmem L;
-  L.stage_cap = (10 * kc > 1024) ? 10 * kc : 1024;  // the lists hold ~6.5 x kc keys (optimistic threshold): stage them all
+  // the lists hold ~6.5 x kc keys (optimistic threshold): stage them all -- 10 x kc slots, fewer when a wide
+  // kc (the 4x kc of a completion pass) would not leave room for the rest (the kernel falls back to its
+  // histogram selection when the stage overflows)
+  const size_t fixed = static_cast<size_t>(kc) * 16 + (static_cast<size_t>(kc) * 4 + 15) / 16 * 16 +
+                       static_cast<size_t>(ld) * 4 + kBins * 4 + (static_cast<size_t>(nlists) + 1) * 4 + 16 + 32 * 4;
+  size_t cap = 10 * static_cast<size_t>(kc) > 1024 ? 10 * static_cast<size_t>(kc) : 1024;
+  const size_t budget = 212 * 1024;
+  if (fixed + cap * 8 > budget && fixed < budget) {
+    const size_t fit = (budget - fixed) / 8;
+    const size_t floor_cap = 2 * static_cast<size_t>(kc) > 1024 ? 2 * static_cast<size_t>(kc) : 1024;
+    cap = fit > floor_cap ? fit : floor_cap;
+  }
+  L.stage_cap = static_cast<int>(cap);
   size_t o = 0;
   L.stage = o; o += static_cast<size_t>(L.stage_cap) * 8;
   L.sel = o; o += static_cast<size_t>(kc) * 8;
@@ -63,6 +75,34 @@ struct TailParams {
   size_t slot_stride;
   char* region[kPeerMax];
   const int64_t* step;
+  // completion launches (second pass over the uncertified queries of a step, device-driven):
+  const int32_t* qmap;    // launch row r answers ORIGINAL query qmap[r]: every output goes to that row
+  const int32_t* active;  // only rows r < *active are live; the others go straight to the done count
+  int commit_certified_only;  // outputs are written only if this launch certifies the query
+  int no_signal;          // peer rows are stored but the arrival signal is left to a later launch
+  int64_t out_rows;       // rows of the output arrays / of the packed peer block (0 = nq)
+};
+
+struct K3Args {
+  const float* q32;
+  const float* g32;
+  int ld;
+  int64_t nq, ng;
+  int k;
+  int64_t idx_offset;
+  int nlists, cap, kc;
+  const int32_t* counts;
+  const uint64_t* cand;
+  const float* thr_out;
+  const float* thr_hi;
+  const float* q_delta;
+  float g_delta_max, eps_acc;
+  float* out_sim;
+  int64_t* out_idx;
+  int32_t* uncert_list;
+  int32_t* state;
+  SelSmem L;
+  TailParams tail;
 };
 
 // Visit every candidate key of this query in batches: the lists of warp w (w, w+W, ...) form a queue
@@ -162,22 +202,32 @@ __device__ __forceinline__ void rank_scatter(const uint64_t* keys, int n, uint64
   }
 }
 
-// kSelThreads: 128 threads x 10 CTAs/SM (k <= 32, many queries: twice as many queries in flight hide the
-// barrier / gather latencies), 256 x 5 in general, 1024 for few queries (streaming regime: the per-query
-// latency IS the kernel time, so the whole CTA width goes to one query).
 #ifndef HCIR_K3_THREADS_PER_SM
 #define HCIR_K3_THREADS_PER_SM 1024  // resident K3 threads per SM the register budget is sized for (A/B: 1280)
 #endif
+// Everything a query's CTA does up to and including its stores into the peers (the kernel below adds the
+// launch-wide done count / arrival signal, which every CTA must reach whether its row is live or not).
 template <int kSelThreads>
-__global__ void __launch_bounds__(kSelThreads, (kSelThreads >= 1024) ? 1 : HCIR_K3_THREADS_PER_SM / kSelThreads)
-select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int ld, int64_t nq,
-                      int64_t ng, int k, int64_t idx_offset, int nlists, int cap, int kc,
-                      const int32_t* __restrict__ counts, const uint64_t* __restrict__ cand,
-                      const float* __restrict__ thr_out, const float* __restrict__ thr_hi,
-                      const float* __restrict__ q_delta, float g_delta_max, float eps_acc,
-                      float* __restrict__ out_sim, int64_t* __restrict__ out_idx,
-                      int32_t* __restrict__ uncert_list, int32_t* __restrict__ state, SelSmem L,
-                      const TailParams tail) {
+__device__ __forceinline__ void select_rescore_body(const K3Args& a, const int64_t q) {
+  const float* __restrict__ q32 = a.q32;
+  const float* __restrict__ g32 = a.g32;
+  const int ld = a.ld;
+  const int64_t nq = a.nq, ng = a.ng;
+  const int k = a.k;
+  const int64_t idx_offset = a.idx_offset;
+  const int nlists = a.nlists, cap = a.cap, kc = a.kc;
+  const int32_t* __restrict__ counts = a.counts;
+  const uint64_t* __restrict__ cand = a.cand;
+  const float* __restrict__ thr_out = a.thr_out;
+  const float* __restrict__ thr_hi = a.thr_hi;
+  const float* __restrict__ q_delta = a.q_delta;
+  const float g_delta_max = a.g_delta_max, eps_acc = a.eps_acc;
+  float* __restrict__ out_sim = a.out_sim;
+  int64_t* __restrict__ out_idx = a.out_idx;
+  int32_t* __restrict__ uncert_list = a.uncert_list;
+  int32_t* __restrict__ state = a.state;
+  const SelSmem& L = a.L;
+  const TailParams& tail = a.tail;
   constexpr int kSelWarps = kSelThreads / kWarp;
   constexpr bool kWide = (kSelThreads >= 1024);
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -191,10 +241,8 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
   uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + L.scratch);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t q = blockIdx.x;
   const int ld4 = ld >> 2;
   const uint64_t* lists = cand + q * nlists * static_cast<int64_t>(cap);
-  pdl_wait();
 
   // ---- start: issue the query-row loads (consumed after the key pass); every warp fetches the
   // lengths / thresholds of ITS lists (w, w+W, ...) and goes straight to reading keys -- there is
@@ -558,60 +606,80 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       res[rank] = mine;
       rsim[rank] = s;
       lab[rank] = clab[t];
-      out_sim[q * k + rank] = s;
-      out_idx[q * k + rank] = static_cast<int64_t>(key_idx(mine)) + idx_offset;
-      if (tail.out_lab) tail.out_lab[q * k + rank] = clab[t];
       if (rank == k - 1) scratch[7] = __float_as_uint(s);
     }
   }
   // fewer than k candidates (the query is uncertified): the missing ranks read (-inf, -1), never stale memory
   for (int j = nr + tid; j < k; j += kSelThreads) {
-    out_sim[q * k + j] = -INFINITY;
-    out_idx[q * k + j] = -1;
+    res[j] = 0ull;
     rsim[j] = -INFINITY;
     lab[j] = -1;
-    if (tail.out_lab) tail.out_lab[q * k + j] = -1;
   }
   __syncthreads();
-  if (tid == 0) {
-    const float sk = (nr >= k) ? __uint_as_float(scratch[7]) : -INFINITY;
-    // rows outside `sel` score <= tprime in bf16 (list thresholds, kc cut), hence <= tprime + eps in fp32
-    const bool certified = (nr >= k) && (tprime + eps < sk);
-    if (!certified) {
-      const int at = atomicAdd(&state[0], 1);
-      HCIR_DEV_CHECK(at >= 0 && at < nq);
-      uncert_list[at] = static_cast<int32_t>(q);
-    }
+  const float sk = (nr >= k) ? __uint_as_float(scratch[7]) : -INFINITY;
+  // rows outside `sel` score <= tprime in bf16 (list thresholds, kc cut), hence <= tprime + eps in fp32
+  const bool certified = (nr >= k) && (tprime + eps < sk);
+  // completion launches answer ORIGINAL query qmap[q] and only commit what they certify (the first pass's
+  // best-so-far answer stays in place otherwise and the query goes to the final uncertified list)
+  const int64_t row = tail.qmap ? static_cast<int64_t>(tail.qmap[q]) : q;
+  const int64_t out_rows = tail.out_rows > 0 ? tail.out_rows : nq;
+  const bool commit = certified || !tail.commit_certified_only;
+  if (tid == 0 && !certified) {
+    const int at = atomicAdd(&state[0], 1);
+    HCIR_DEV_CHECK(at >= 0 && at < out_rows);
+    uncert_list[at] = static_cast<int32_t>(row);
+  }
+  if (!commit) return;   // block-uniform; the caller still runs the done count
+  const int nres = nr < k ? nr : k;  // (< k only for uncertified queries, which are completed later)
+  for (int j = tid; j < k; j += kSelThreads) {
+    out_sim[row * k + j] = rsim[j];
+    out_idx[row * k + j] = (j < nres) ? static_cast<int64_t>(key_idx(res[j])) + idx_offset : -1;
+    if (tail.out_lab) tail.out_lab[row * k + j] = lab[j];
   }
 
-  // ======================= tail: labels -> vote -> peers -> arrival =======================
-  const int nres = nr < k ? nr : k;  // (< k only for uncertified queries, which are completed later)
+  // ======================= tail: vote -> peers =======================
   int64_t pred_val = 0;
   const bool do_vote = (tail.pred != nullptr) || (tail.payload == 2);
   if (do_vote && warp == 0) {
     const int best_c = warp_vote(rsim, lab, nres, tail.num_classes, tail.T, lane);
     pred_val = tail.classes ? tail.classes[best_c] : static_cast<int64_t>(best_c);
-    if (lane == 0 && tail.pred) tail.pred[q] = pred_val;
+    if (lane == 0 && tail.pred) tail.pred[row] = pred_val;
   }
   if (tail.world > 0) {
     // this query's results go straight into slot (parity of this step, rank) of EVERY rank's region
     const int64_t st = *tail.step + 1;
     const size_t slot_off = kPeerHdrBytes + (static_cast<size_t>(st & 1) * tail.world + tail.rank) * tail.slot_stride;
     if (tail.payload == 1) {
-      const size_t e = static_cast<size_t>(nq) * k;
+      const size_t e = static_cast<size_t>(out_rows) * k;
       for (int i = tid; i < k * tail.world; i += kSelThreads) {
         const int g = i / k, j = i - g * k;
         char* base = tail.region[g] + slot_off;
-        const size_t at = static_cast<size_t>(q) * k + j;
+        const size_t at = static_cast<size_t>(row) * k + j;
         const uint64_t key = (j < nres) ? res[j] : 0ull;
         reinterpret_cast<int64_t*>(base)[at] = (j < nres) ? static_cast<int64_t>(key_idx(key)) + idx_offset : -1;
         reinterpret_cast<float*>(base + e * 8)[at] = (j < nres) ? key_sim(key) : -INFINITY;
         if (tail.labels) reinterpret_cast<int32_t*>(base + e * 12)[at] = lab[j];
       }
     } else if (tail.payload == 2) {
-      if (warp == 0 && lane < tail.world) reinterpret_cast<int64_t*>(tail.region[lane] + slot_off)[q] = pred_val;
+      if (warp == 0 && lane < tail.world) reinterpret_cast<int64_t*>(tail.region[lane] + slot_off)[row] = pred_val;
     }
   }
+}
+
+// kSelThreads: 128 threads (k <= 32, many queries: twice as many queries in flight hide the barrier / gather
+// latencies), 256 in general, 1024 for few queries (streaming regime: the per-query latency IS the kernel
+// time, so the whole CTA width goes to one query).
+template <int kSelThreads>
+__global__ void __launch_bounds__(kSelThreads, (kSelThreads >= 1024) ? 1 : HCIR_K3_THREADS_PER_SM / kSelThreads)
+select_rescore_kernel(const __grid_constant__ K3Args a) {
+  pdl_wait();
+  const int64_t q = blockIdx.x;
+  const TailParams& tail = a.tail;
+  int32_t* state = a.state;
+  const int64_t nq = a.nq;
+  const int tid = threadIdx.x;
+  const bool live = (tail.active == nullptr) || (q < static_cast<int64_t>(*tail.active));
+  if (live) select_rescore_body<kSelThreads>(a, q);
   // ---- last CTA of the launch: publish the uncertified count, reset the counters, signal the peers ----
   __syncthreads();
   if (tid == 0) {
@@ -622,7 +690,7 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       const int n_unc = atomicExch(&state[0], 0);
       state[1] = n_unc;
       state[2] = 0;
-      if (tail.world > 0) {
+      if (tail.world > 0 && !tail.no_signal) {
         const int64_t st = *tail.step + 1;
         const size_t par = static_cast<size_t>(st & 1);
         for (int g = 0; g < tail.world; ++g)
@@ -634,6 +702,48 @@ select_rescore_kernel(const float* __restrict__ q32, const float* __restrict__ g
       }
     }
   }
+}
+
+// ---- device-driven completion, step 1: the compact batch of uncertified queries --------------------
+// grid = capacity CTAs (one per compact row) + grid-stride over the overflow; block 128.
+__global__ void __launch_bounds__(128)
+retry_setup_kernel(const uint16_t* __restrict__ qbf, const float* __restrict__ q32, const float* __restrict__ qdl,
+                   int ld, int64_t nq, int k, const float* __restrict__ out_sim,
+                   const int32_t* __restrict__ unc_list, const int32_t* __restrict__ unc_state, float g_delta_max,
+                   float eps_acc, int capacity, uint16_t* __restrict__ q2bf, float* __restrict__ q2f,
+                   float* __restrict__ q2d, float* __restrict__ thr0, float* __restrict__ thr_hi,
+                   int32_t* __restrict__ qmap, int32_t* __restrict__ active, int32_t* __restrict__ final_list,
+                   int32_t* __restrict__ final_state) {
+  pdl_wait();
+  const int count = unc_state[1];  // uncertified queries of the first pass
+  const int n = count < capacity ? count : capacity;
+  const int r = blockIdx.x;
+  if (r == 0 && threadIdx.x == 0) *active = n;
+  if (r < n) {
+    const int64_t q = unc_list[r];
+    const uint4* sb = reinterpret_cast<const uint4*>(qbf + q * ld);
+    uint4* db = reinterpret_cast<uint4*>(q2bf + static_cast<int64_t>(r) * ld);
+    for (int c = threadIdx.x; c < ld / 8; c += blockDim.x) db[c] = sb[c];
+    const float4* sf = reinterpret_cast<const float4*>(q32 + q * ld);
+    float4* df = reinterpret_cast<float4*>(q2f + static_cast<int64_t>(r) * ld);
+    for (int c = threadIdx.x; c < ld / 4; c += blockDim.x) df[c] = sf[c];
+    if (threadIdx.x == 0) {
+      const float dq = qdl ? qdl[q] : 0.0f;
+      const float eps = g_delta_max * (1.0f + dq) + dq * (1.0f + 1e-6f) + eps_acc;
+      // every true top-k row scores >= s_k in fp32, hence > s_k - eps in the bf16 contraction
+      const float t = out_sim[q * k + (k - 1)] - eps * 1.001f - 1e-6f;
+      q2d[r] = dq;
+      thr0[r] = t;
+      thr_hi[r] = t;
+      qmap[r] = static_cast<int32_t>(q);
+    }
+  } else if (threadIdx.x == 0) {
+    thr0[r] = INFINITY;  // nothing passes; the row's K3 CTA is not live
+    thr_hi[r] = INFINITY;
+  }
+  // more uncertified queries than the batch holds: they go straight to the final list (host completion)
+  for (int i = capacity + blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    final_list[atomicAdd(&final_state[0], 1)] = unc_list[i];
 }
 
 static int launch_select(const float* q_f32, const float* g_f32, int ld, int64_t nq, int64_t ng, int k,
@@ -671,9 +781,17 @@ static int launch_select(const float* q_f32, const float* g_f32, int ld, int64_t
     tp.payload = tail->world > 0 ? tail->payload : 0;
     tp.slot_stride = (tail->slot_bytes + 255) / 256 * 256;
     tp.step = tail->step;
+    tp.qmap = tail->qmap;
+    tp.active = tail->active;
+    tp.commit_certified_only = tail->commit_certified_only;
+    tp.no_signal = tail->no_signal;
+    tp.out_rows = tail->out_rows;
+    HCIR_REQUIRE(tail->out_rows >= 0 && (tail->qmap != nullptr || tail->out_rows == 0 || tail->out_rows == nq),
+                 "select_rescore: out_rows without a query map");
     if (tail->world > 0) {
-      const size_t need = tail->payload == 1 ? hcir_packed_block_bytes(nq, k, tail->labels != nullptr ? 1 : 0)
-                                             : static_cast<size_t>(nq) * 8;
+      const int64_t rows = tail->out_rows > 0 ? tail->out_rows : nq;
+      const size_t need = tail->payload == 1 ? hcir_packed_block_bytes(rows, k, tail->labels != nullptr ? 1 : 0)
+                                             : static_cast<size_t>(rows) * 8;
       HCIR_REQUIRE(need <= tail->slot_bytes, "select_rescore: peer slot of %zu bytes is smaller than the %zu-byte block",
                    static_cast<size_t>(tail->slot_bytes), need);
       for (int g = 0; g < tail->world; ++g) {
@@ -702,10 +820,32 @@ static int launch_select(const float* q_f32, const float* g_f32, int ld, int64_t
     HCIR_CUDA_TRY(cudaFuncSetAttribute(select_rescore_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                        static_cast<int>(L.total)));                                                \
     HCIR_CUDA_TRY(launch_pdl(select_rescore_kernel<T_>, dim3(static_cast<unsigned>(nq)), dim3(T_), L.total, st,    \
-                             q_f32, g_f32, ld, nq, ng, k, idx_offset, plan->nlists, plan->cap, plan->kc, counts,   \
-                             cand, thr_out, thr_hi, q_delta, g_delta_max, eps_acc, out_sim, out_idx, uncert_list,  \
-                             state, L, tp));                                                                       \
+                             args));                                                                               \
   } while (0)
+  K3Args args{};
+  args.q32 = q_f32;
+  args.g32 = g_f32;
+  args.ld = ld;
+  args.nq = nq;
+  args.ng = ng;
+  args.k = k;
+  args.idx_offset = idx_offset;
+  args.nlists = plan->nlists;
+  args.cap = plan->cap;
+  args.kc = plan->kc;
+  args.counts = counts;
+  args.cand = cand;
+  args.thr_out = thr_out;
+  args.thr_hi = thr_hi;
+  args.q_delta = q_delta;
+  args.g_delta_max = g_delta_max;
+  args.eps_acc = eps_acc;
+  args.out_sim = out_sim;
+  args.out_idx = out_idx;
+  args.uncert_list = uncert_list;
+  args.state = state;
+  args.L = L;
+  args.tail = tp;
   // CTA width: forced by the plan flags (measurement aid) or chosen from the shape
   const int width = (plan->flags & HCIR_FLAG_K3_WIDTH_MASK) >> HCIR_FLAG_K3_WIDTH_SHIFT;
   if (width == 3 || (width == 0 && nq <= 2 * static_cast<int64_t>(sms))) HCIR_LAUNCH_SEL(1024);
@@ -725,4 +865,24 @@ extern "C" int hcir_select_rescore(const float* q_f32, const float* g_f32, int l
                                    const hcir_tail_t* tail, hcir_stream_t stream) {
   return hcir::launch_select(q_f32, g_f32, ld, nq, ng, k, idx_offset, plan, workspace, q_delta, g_delta_max, eps_acc,
                              out_sim, out_idx, uncert_list, uncert_state, tail, stream);
+}
+
+extern "C" int hcir_retry_setup(const uint16_t* q_bf16, const float* q_f32, const float* q_delta, int ld, int64_t nq,
+                                int k, const float* out_sim, const int32_t* uncert_list, const int32_t* uncert_state,
+                                float g_delta_max, float eps_acc, int capacity, uint16_t* q2_bf16, float* q2_f32,
+                                float* q2_delta, float* thr0_2, float* thr_hi_2, int32_t* qmap, int32_t* active,
+                                int32_t* final_list, int32_t* final_state, hcir_stream_t stream) {
+  using namespace hcir;
+  HCIR_REQUIRE(ld > 0 && ld % 64 == 0 && nq > 0 && k > 0 && capacity > 0 && capacity <= 4096,
+               "retry_setup: bad shape ld=%d nq=%lld k=%d capacity=%d", ld, (long long)nq, k, capacity);
+  HCIR_REQUIRE(q_bf16 && q_f32 && out_sim && uncert_list && uncert_state && q2_bf16 && q2_f32 && q2_delta && thr0_2 &&
+                   thr_hi_2 && qmap && active && final_list && final_state,
+               "retry_setup: null pointer");
+  int rc = check_device();
+  if (rc != HCIR_OK) return rc;
+  HCIR_CUDA_TRY(launch_pdl(retry_setup_kernel, dim3(static_cast<unsigned>(capacity)), dim3(128), 0,
+                           static_cast<cudaStream_t>(stream), q_bf16, q_f32, q_delta, ld, nq, k, out_sim, uncert_list,
+                           uncert_state, g_delta_max, eps_acc, capacity, q2_bf16, q2_f32, q2_delta, thr0_2, thr_hi_2, qmap,
+                           active, final_list, final_state));
+  return HCIR_OK;
 }

@@ -73,6 +73,7 @@ struct SimParams {
   float* dump;        // [nq][ng]          debug: raw accumulator values
   float* cmax;        // [nq][num_chunks]  sample: maxima of `chunk_w` consecutive sample columns
   int chunk_w, num_chunks;
+  const int32_t* active;  // gated launch (device-driven completion): every CTA returns at once if *active == 0
 };
 
 enum : int { kModeMain = 0, kModeDump = 1, kModeSample = 2 };
@@ -143,6 +144,10 @@ simtopk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                const SimParams p) {
   constexpr int kStages = SimCfg<kCtas>::kStages;
   constexpr int kBBytesCta = SimCfg<kCtas>::kBBytesCta;
+  if (p.active != nullptr) {  // uniform over the grid; nothing has been set up yet
+    pdl_wait();
+    if (*p.active == 0) return;
+  }
   extern __shared__ uint8_t smem_dyn[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment; align by hand, do not trust the base.
   // (Both CTAs of a pair see the same offset: the dynamic smem base is the same in every CTA.)
@@ -731,7 +736,8 @@ static int launch_mode(const CUtensorMap& mq, const CUtensorMap& mg, SimParams p
 }
 
 static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng, int ld,
-                          const hcir_plan_t* plan, void* workspace, float* dump, cudaStream_t st) {
+                          const hcir_plan_t* plan, void* workspace, float* dump, cudaStream_t st,
+                          const int32_t* active = nullptr) {
   HCIR_REQUIRE(plan != nullptr && workspace != nullptr, "simtopk: null plan/workspace");
   HCIR_REQUIRE(q_bf16 && g_bf16, "simtopk: null operand");
   HCIR_REQUIRE(ld > 0 && ld % 64 == 0, "simtopk: ld=%d must be a positive multiple of 64", ld);
@@ -831,6 +837,7 @@ static int launch_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_
   p.thr_out = reinterpret_cast<float*>(ws + plan->thr_out_off);
   p.dump = dump;
   p.flags = plan->flags;
+  p.active = active;
   if (pairs)
     return dump != nullptr ? launch_mode<kModeDump, 2>(mq, mg, p, sms, st) : launch_mode<kModeMain, 2>(mq, mg, p, sms, st);
   return dump != nullptr ? launch_mode<kModeDump, 1>(mq, mg, p, sms, st) : launch_mode<kModeMain, 1>(mq, mg, p, sms, st);
@@ -930,6 +937,16 @@ extern "C" int hcir_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* 
                             const hcir_plan_t* plan, void* workspace, hcir_stream_t stream) {
   return hcir::launch_simtopk(q_bf16, nq, g_bf16, ng, ld, plan, workspace, nullptr,
                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hcir_simtopk_gated(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng, int ld,
+                                  const hcir_plan_t* plan, void* workspace, const int32_t* active,
+                                  hcir_stream_t stream) {
+  using namespace hcir;
+  HCIR_REQUIRE(active != nullptr, "simtopk_gated: null count");
+  HCIR_REQUIRE(plan != nullptr && (plan->flags & HCIR_FLAG_MAIN_ONLY),
+               "simtopk_gated: only the main pass can be gated (set HCIR_FLAG_MAIN_ONLY)");
+  return launch_simtopk(q_bf16, nq, g_bf16, ng, ld, plan, workspace, nullptr, static_cast<cudaStream_t>(stream), active);
 }
 
 extern "C" int hcir_simtopk_debug(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng, int ld,

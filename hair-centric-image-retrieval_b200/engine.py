@@ -619,8 +619,10 @@ class SearchSession:
     channel is allocated collectively on the eager warm-up pass); ``post(session)`` enqueues what
     follows K3 in the same graph (the fused wait + merge + vote kernel, or the wait kernel)."""
 
+    RETRY_CAPACITY = 128   # queries the in-graph completion pass holds (one query tile)
+
     def __init__(self, bank: "GalleryBank", nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False,
-                 pack: bool = False, post=None, tail_hook=None, trailer: bool = False):
+                 pack: bool = False, post=None, tail_hook=None, trailer: bool = False, device_completion=None):
         if not (1 <= k <= bank.n):
             raise ValueError(f"k={k} must be in [1, N={bank.n}]")
         if vote and bank.labels is None:
@@ -637,9 +639,19 @@ class SearchSession:
         self._profile = profile
         with torch.cuda.device(dev):
             self.q_in = torch.zeros((self.nq, bank.d), dtype=torch.float32, device=dev)
-            # K3's counters: zero once, the kernel leaves [0] and [2] at zero after every launch
-            self.unc_state = torch.zeros((4,), dtype=torch.int32, device=dev)
-            self.unc_cnt = self.unc_state[1:2]   # result of the last launch
+            # K3's counters: zero once, the kernel leaves [0] and [2] at zero after every launch.
+            # [0:4] first pass, [4:8] the completion pass (device_completion)
+            self.counters = torch.zeros((8,), dtype=torch.int32, device=dev)
+            self.unc_state = self.counters[0:4]
+            self.final_state = self.counters[4:8]
+            # Device-driven completion: the second tensor pass over the uncertified queries is part of the
+            # graph (three more kernels that return at once when nothing is uncertified), so a step whose
+            # queries the second pass can certify needs no host action at all.  On by default from k = 128
+            # (at k = 200 some query of every 16k-query step is uncertified); the ~10 us of idle launches are
+            # not worth it for small k, where uncertified queries are rare and steps short.
+            self.dev_completion = (k >= 128) if device_completion is None else bool(device_completion)
+            # what the host reads after a replay: queries that are STILL uncertified
+            self.unc_cnt = self.final_state[1:2] if self.dev_completion else self.unc_state[1:2]
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -650,8 +662,19 @@ class SearchSession:
             # a captured collective: NCCL's watchdog thread polls CUDA events while we capture, which
             # only the thread-local capture mode tolerates
             mode = "thread_local" if post is not None else "global"
-            with torch.cuda.graph(self.graph, capture_error_mode=mode):
-                self._body(capture=True)
+            # Python's cyclic collector must not run inside the capture: an earlier session is garbage only
+            # through the bank <-> session cycle, and destroying its CUDA graph (cudaGraphExecDestroy) while
+            # this thread captures in global mode invalidates the capture (seen as error 901 on the next
+            # launch).  torch.cuda.graph collects before it begins; nothing may be collected until it ends.
+            import gc
+            gc_was = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(self.graph, capture_error_mode=mode):
+                    self._body(capture=True)
+            finally:
+                if gc_was:
+                    gc.enable()
         self.launches_per_run = 1  # one graph launch; the kernels inside: self.kernels_per_run
 
     def _mark(self, name, capture):
@@ -716,6 +739,8 @@ class SearchSession:
             tail.out_lab = self.out_lab.data_ptr()
         if self.tail_hook is not None:
             self.tail_hook(self, tail)
+        if self.dev_completion and tail.world > 0:
+            tail.no_signal = 1   # the completion pass may still correct rows: IT signals the peers
         _lib.check(lib.hcir_select_rescore(self.q32.data_ptr(), b.g32.data_ptr(), b.ld, nq, b.n, k, b.idx_offset,
                                            plan, self.ws.data_ptr(), self.qdl.data_ptr(), b.g_delta_max, b.eps_acc,
                                            self.out_sim.data_ptr(), self.out_idx.data_ptr(),
@@ -724,11 +749,73 @@ class SearchSession:
         plan.flags = 0
         self._mark("t3", capture)
         kernels += 2
+        self.final_list = self.unc_list
+        if self.dev_completion:
+            kernels += self._completion_pass(tail, st)
         if self.trailer:
             self.pack[self.block_bytes: self.block_bytes + 4].view(torch.int32).copy_(self.unc_cnt)
         if self.post is not None:
             self.post_out = self.post(self)
         self.kernels_per_run = kernels
+
+    def _completion_pass(self, tail, st) -> int:
+        """In-graph second pass over the queries K3 could not certify (GalleryBank._finish_uncertified has
+        the reasoning): gather them into a compact batch with explicit thresholds (hcir_retry_setup), stream
+        the gallery once for that batch if there is one (hcir_simtopk_gated), and let K3 -- same tail, rows
+        mapped back to the original queries -- overwrite what it certifies, signal the peers, and list what
+        is STILL uncertified (near-duplicate galleries) for the exact kernel on the host's initiative."""
+        b, lib, dev = self.bank, self.bank.lib, self.bank.device
+        R, k = self.RETRY_CAPACITY, self.k
+        kc = b.choose_kc(k)
+        plan2 = Plan()
+        for mult in (4, 3, 2, 1):   # widest kc whose plan still carries per-query thresholds
+            kc2 = max(kc, min(mult * kc, 2048))
+            _lib.check(lib.hcir_simtopk_plan(R, b.n, b.ld, kc2, b.sm_count, plan2), "simtopk_plan")
+            if plan2.sample_rows > 0:
+                break
+        if plan2.sample_rows <= 0:   # (cannot happen on the tensor path: the gallery is big enough for a sample)
+            self.dev_completion = False
+            self.unc_cnt = self.unc_state[1:2]
+            return 0
+        plan2.q_rows = R
+        self.plan2 = plan2
+        if getattr(self, "ws2", None) is None:
+            # allocated once, on the eager warm-up pass (nothing here needs initialising: the setup kernel
+            # writes every threshold, rows beyond the live count get +inf and are never read back) -- a
+            # torch.zeros inside the capture would put a fill node of the whole workspace into the graph
+            self.ws2 = torch.empty((int(plan2.bytes),), dtype=torch.uint8, device=dev)
+            self.q2bf = torch.empty((R, b.ld), dtype=torch.bfloat16, device=dev)
+            self.q2f = torch.empty((R, b.ld), dtype=torch.float32, device=dev)
+            self.q2d = torch.empty((R,), dtype=torch.float32, device=dev)
+            self.qmap = torch.empty((R,), dtype=torch.int32, device=dev)
+            self.retry_active = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self._final_list = torch.empty((self.nq,), dtype=torch.int32, device=dev)
+        self.final_list = self._final_list
+        _lib.check(lib.hcir_retry_setup(self.qbf.data_ptr(), self.q32.data_ptr(), self.qdl.data_ptr(), b.ld, self.nq, k,
+                                        self.out_sim.data_ptr(), self.unc_list.data_ptr(), self.unc_state.data_ptr(),
+                                        b.g_delta_max, b.eps_acc, R, self.q2bf.data_ptr(), self.q2f.data_ptr(),
+                                        self.q2d.data_ptr(), self.ws2.data_ptr() + int(plan2.thr0_off),
+                                        self.ws2.data_ptr() + int(plan2.thr_hi_off), self.qmap.data_ptr(),
+                                        self.retry_active.data_ptr(), self.final_list.data_ptr(),
+                                        self.final_state.data_ptr(), st), "retry_setup")
+        plan2.flags = 4  # HCIR_FLAG_MAIN_ONLY: the thresholds are in the workspace
+        _lib.check(lib.hcir_simtopk_gated(self.q2bf.data_ptr(), R, b.gbf.data_ptr(), b.n, b.ld, plan2,
+                                          self.ws2.data_ptr(), self.retry_active.data_ptr(), st), "simtopk(completion)")
+        plan2.flags = 0
+        t2 = Tail()
+        for name, _ in Tail._fields_:   # same labels / vote / peers as the first pass ...
+            setattr(t2, name, getattr(tail, name))
+        t2.no_signal = 0                # ... but this launch signals, commits only what it certifies,
+        t2.commit_certified_only = 1    # and writes to the rows of the original queries
+        t2.qmap = self.qmap.data_ptr()
+        t2.active = self.retry_active.data_ptr()
+        t2.out_rows = self.nq
+        _lib.check(lib.hcir_select_rescore(self.q2f.data_ptr(), b.g32.data_ptr(), b.ld, R, b.n, k, b.idx_offset, plan2,
+                                           self.ws2.data_ptr(), self.q2d.data_ptr(), b.g_delta_max, b.eps_acc,
+                                           self.out_sim.data_ptr(), self.out_idx.data_ptr(),
+                                           self.final_list.data_ptr(), self.final_state.data_ptr(), t2, st),
+                   "select_rescore(completion)")
+        return 3
 
     def _gather_packed_labels(self):
         b = self.bank
@@ -750,9 +837,16 @@ class SearchSession:
         return out
 
     def finish_uncertified(self, n_unc: int):
-        """Eager completion of the (rare) queries the tensor path could not certify."""
+        """Eager completion of the (rare) queries the tensor path could not certify: the second tensor pass
+        and then the exact kernel -- or, when the second pass already ran inside the graph
+        (device_completion), only the exact kernel for what it left."""
         b = self.bank
-        b._finish_uncertified(self.q32, self.qbf, self.qdl, self.unc_list, n_unc, self.k, self.out_sim, self.out_idx)
+        if self.dev_completion:
+            b._exact(self.q32, self.final_list, n_unc, self.k, self.out_sim, self.out_idx)
+            b.retry_stats = {"second_pass": "in graph", "exact": int(n_unc)}
+        else:
+            b._finish_uncertified(self.q32, self.qbf, self.qdl, self.unc_list, n_unc, self.k, self.out_sim,
+                                  self.out_idx)
         if self.out_lab is not None:
             self._gather_packed_labels()
 
@@ -815,16 +909,16 @@ class SearchSession:
             b.launches += self.kernels_per_run
             if not check:
                 return self.pred, self.out_sim, self.out_idx
-            n_unc = int(self.unc_cnt.item())
+            cnt = self.counters.tolist()   # one 32-byte read-back: [1] first pass, [5] after the in-graph completion
+            n_unc = cnt[5] if self.dev_completion else cnt[1]
             pred = self.pred
             if n_unc > 0:
-                b._finish_uncertified(self.q32, self.qbf, self.qdl, self.unc_list, n_unc, self.k, self.out_sim,
-                                      self.out_idx)
+                self.finish_uncertified(n_unc)
                 if self.vote:
                     pred = self._tail()
-                elif self.out_lab is not None:
-                    self._gather_packed_labels()
-            b.last_stats = {"path": "tensor+graph", "uncertified": n_unc, "nsplit": int(self.plan.nsplit),
+            b.last_stats = {"path": "tensor+graph", "uncertified": n_unc, "uncertified_first_pass": cnt[1],
+                            "completion": "device" if self.dev_completion else "host",
+                            "nsplit": int(self.plan.nsplit),
                             "kc": int(self.plan.kc), "cap": int(self.plan.cap),
                             "workspace_bytes": int(self.plan.bytes), "sample_rows": int(self.plan.sample_rows),
                             "chunk_w": int(self.plan.chunk_w)}
@@ -832,11 +926,12 @@ class SearchSession:
 
 
 def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: bool = False, pack: bool = False,
-                  post=None, post_key=None, tail_hook=None, trailer: bool = False):
+                  post=None, post_key=None, tail_hook=None, trailer: bool = False, device_completion=None):
     """Cached :class:`SearchSession` for this shape, or None if the exact path would be used."""
     if nq < 1 or not self.use_tensor_path(nq, k):
         return None
-    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile), bool(pack), post_key)
+    key = (int(nq), int(k), None if T is None else float(T), bool(vote), bool(profile), bool(pack), post_key,
+           device_completion)
     # Sessions whose graph ends in a multi-GPU exchange own a collectively constructed channel: they
     # live in their own cache, whose keys hold rank-independent values only, so every rank creates
     # and evicts them at the same calls (rank-local sessions can never shift that order).
@@ -849,7 +944,7 @@ def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: 
             if xc is not None:   # every rank evicts the same session at the same call -> collective close
                 xc.close()
         s = cache[key] = SearchSession(self, nq, k, T=T, vote=vote, profile=profile, pack=pack, post=post,
-                                       tail_hook=tail_hook, trailer=trailer)
+                                       tail_hook=tail_hook, trailer=trailer, device_completion=device_completion)
     return s
 
 

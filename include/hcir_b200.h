@@ -122,6 +122,11 @@ typedef struct {
 int hcir_simtopk_plan(int64_t nq, int64_t ng, int ld, int kc, int sm_count, hcir_plan_t* plan);
 int hcir_simtopk(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng, int ld,
                  const hcir_plan_t* plan, void* workspace, hcir_stream_t stream);
+/* The same launch gated by a device-side count: every CTA returns at once when *active == 0
+ * (the second pass of a device-driven completion: it streams the gallery only if a query needs it). */
+int hcir_simtopk_gated(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng, int ld,
+                       const hcir_plan_t* plan, void* workspace, const int32_t* active,
+                       hcir_stream_t stream);
 /* Debug / test entry: same kernel, additionally dumps the raw fp32 accumulator tile values
  * to scores[nq][ng] (row-major).  Only for small problems. */
 int hcir_simtopk_debug(const uint16_t* q_bf16, int64_t nq, const uint16_t* g_bf16, int64_t ng,
@@ -171,6 +176,12 @@ typedef struct {
   uint64_t slot_bytes;     /* the channel's slot size (hcir_peer_region_bytes)                      */
   void* regions[HCIR_PEER_MAX]; /* every rank's region as mapped HERE, own region included          */
   const int64_t* step;     /* the channel's completed-step counter (device)                        */
+  /* completion launches (hcir_retry_setup below): */
+  const int32_t* qmap;     /* launch row r answers ORIGINAL query qmap[r]; outputs go to that row   */
+  const int32_t* active;   /* device count: only rows r < *active are live (the rest just count)    */
+  int32_t commit_certified_only; /* write outputs only for queries this launch certifies            */
+  int32_t no_signal;       /* store the peer rows but leave the arrival signal to a later launch    */
+  int64_t out_rows;        /* rows of the output arrays / packed peer block (0 = nq)                */
 } hcir_tail_t;
 
 int hcir_select_rescore(const float* q_f32, const float* g_f32, int ld, int64_t nq, int64_t ng,
@@ -178,6 +189,25 @@ int hcir_select_rescore(const float* q_f32, const float* g_f32, int ld, int64_t 
                         const float* q_delta, float g_delta_max, float eps_acc, float* out_sim,
                         int64_t* out_idx, int32_t* uncert_list, int32_t* uncert_state,
                         const hcir_tail_t* tail, hcir_stream_t stream);
+
+/* Device-driven completion, step 1 of 3 (then hcir_simtopk_gated with HCIR_FLAG_MAIN_ONLY, then
+ * hcir_select_rescore with tail.qmap / tail.active / tail.commit_certified_only): gather the queries a
+ * first pass could not certify (uncert_list[0 .. uncert_state[1])) into a compact batch of at most
+ * `capacity` rows and give each an explicit threshold -- its best-so-far fp32 k-th score minus eps:
+ * every true top-k row scores above it in the bf16 contraction, so the second pass collects all that
+ * can matter and certifies against that very threshold.  Replaces the host-driven gather / scatter of
+ * round 1 (torch fancy indexing + two read-backs): the host looks at ONE count per step, after the
+ * completion, and only near-duplicate galleries ever make it non-zero.
+ *   q2_* / thr2 / qmap   the compact batch (rows >= the count: threshold +inf, nothing passes)
+ *   active[0]            min(count, capacity): gates the two launches that follow
+ *   final_list/final_state  queries beyond `capacity` go straight to the final uncertified list
+ *                           (final_state is the uncert_state of the completion's hcir_select_rescore) */
+int hcir_retry_setup(const uint16_t* q_bf16, const float* q_f32, const float* q_delta, int ld, int64_t nq,
+                     int k, const float* out_sim, const int32_t* uncert_list,
+                     const int32_t* uncert_state, float g_delta_max, float eps_acc, int capacity,
+                     uint16_t* q2_bf16, float* q2_f32, float* q2_delta, float* thr0_2, float* thr_hi_2,
+                     int32_t* qmap, int32_t* active, int32_t* final_list, int32_t* final_state,
+                     hcir_stream_t stream);
 
 /* Exact fp32 path (CUDA cores): brute-force canonical fp32 similarities + exact top-k in
  * canonical order for the queries listed in qlist[0..nlist) (qlist == NULL: queries

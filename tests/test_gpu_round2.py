@@ -283,6 +283,109 @@ def test_peer_prediction_payload_and_wait_kernel_with_fake_ranks():
     peers.close()
 
 
+# ------------------------------------------------------------------------------------ device-driven completion
+def _dense_cluster_case(seed=11, nbase=8, per=300, n_other=20000, d=256, nq=32):
+    g = torch.Generator().manual_seed(seed)
+    bases = torch.randn(nbase, d, generator=g)
+    dense = (bases[:, None, :] + 1e-3 * torch.randn(nbase, per, d, generator=g)).reshape(-1, d)
+    n = n_other + nbase * per
+    bank = torch.cat([torch.randn(n_other, d, generator=g), dense])[torch.randperm(n, generator=g)]
+    qs = bases.repeat_interleave(nq // nbase, 0) + 1e-3 * torch.randn(nq, d, generator=g)
+    return bank, qs
+
+
+@pytest.mark.parametrize("vote", [False, True])
+def test_device_driven_completion_runs_the_second_pass_inside_the_graph(vote):
+    """300 near-identical neighbours per query: the first pass cannot certify the fp32 top-10; with
+    device_completion the second tensor pass (gather -> gated main pass -> K3 on the compact batch, rows
+    mapped back) is part of the graph, resolves every query, and the host finds NOTHING left to do."""
+    bank, qs = _dense_cluster_case()
+    labels = torch.arange(bank.shape[0]) % 7 * 3 + 1
+    gb = GalleryBank(bank, labels)
+    sess = SearchSession(gb, 32, 10, vote=vote, T=0.07 if vote else None, device_completion=True)
+    assert sess.kernels_per_run == 8                      # 5 + setup, gated main pass, K3 on the batch
+    for rep in range(2):
+        pred, sims, idx = sess.run(qs.cuda())
+        st = gb.last_stats
+        assert st["completion"] == "device" and st["uncertified_first_pass"] > 0 and st["uncertified"] == 0, st
+        s2, i2 = gb.topk(qs, 10, mode="exact")
+        assert torch.equal(idx.cpu(), i2) and torch.equal(sims.cpu(), s2)
+        if vote:
+            assert torch.equal(pred.cpu(), gb.predict(qs, 10, T=0.07, mode="exact"))
+        assert sess.counters.tolist()[4:] == [0, 0, 0, 0]
+    # another batch through the same graph (few or no uncertified queries: the gated kernels mostly idle)
+    easy, _ = synth.make_clustered(32, 256, 5, 7)
+    _, sims, idx = sess.run(easy.cuda())
+    assert gb.last_stats["uncertified"] == 0 and gb.last_stats["uncertified_first_pass"] < 8, gb.last_stats
+    s2, i2 = gb.topk(easy, 10, mode="exact")
+    assert torch.equal(idx.cpu(), i2) and torch.equal(sims.cpu(), s2)
+
+
+def test_device_driven_completion_leaves_near_duplicates_and_overflow_to_the_exact_kernel():
+    """A near-duplicate gallery defeats the second pass too, and 256 uncertified queries exceed the
+    128-row completion batch: both kinds end on the final list and are finished by the exact kernel."""
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(1, 256, generator=g)
+    gb = GalleryBank(base + 1e-4 * torch.randn(8192, 256, generator=g), torch.arange(8192) % 5)
+    qd = base + 1e-4 * torch.randn(256, 256, generator=g)
+    sess = SearchSession(gb, 256, 10, device_completion=True)
+    pred, sims, idx = sess.run(qd.cuda())
+    st = gb.last_stats
+    assert st["uncertified_first_pass"] == 256 and st["uncertified"] == 256 and gb.retry_stats["exact"] == 256, st
+    s2, i2 = gb.topk(qd, 10, mode="exact")
+    assert torch.equal(idx.cpu(), i2) and torch.equal(sims.cpu(), s2)
+    assert torch.equal(pred.cpu(), gb.predict(qd, 10, mode="exact"))
+
+
+def test_device_driven_completion_corrects_the_peer_rows_before_the_signal():
+    """Fake ranks on one GPU, device completion on: the first K3 stores its rows but does not signal; the
+    completion K3 overwrites the rows it certifies and signals -- the consumer merges CORRECT rows without
+    any host-side repair or second exchange."""
+    from hcir_b200.sharded import ShardPlan
+    lib = _lib.load()
+    G, k, nq = 2, 10, 32
+    bank, qs = _dense_cluster_case(seed=21)
+    n = bank.shape[0]
+    bl = torch.arange(n) % 9
+    full = GalleryBank(bank, bl, classes=np.arange(9))
+    sp = ShardPlan(n, G)
+    shards = [GalleryBank(bank[sp.start(r):sp.stop(r)], bl[sp.start(r):sp.stop(r)], idx_offset=sp.start(r),
+                          classes=np.arange(9)) for r in range(G)]
+    block = int(lib.hcir_packed_block_bytes(nq, k, 1))
+    peers = FakePeers(G, block)
+    sessions = [SearchSession(sh, nq, k, vote=False, pack=True, device_completion=True,
+                              tail_hook=lambda s_, t_, r=r: peers.fill_tail(t_, r, _lib.PAYLOAD_BLOCK))
+                for r, sh in enumerate(shards)]
+    o_s = torch.empty((nq, k), device="cuda")
+    o_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    o_l = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    pred = torch.empty((nq,), dtype=torch.int64, device="cuda")
+    cls = full._classes_device()
+
+    def consume(r):
+        _lib.check(lib.hcir_peer_merge_vote(peers.ptrs[r], G, nq, k, 1, block, peers.steps[r].data_ptr(), int(20e9),
+                                            o_s.data_ptr(), o_i.data_ptr(), o_l.data_ptr(), 9, 0.0, cls.data_ptr(),
+                                            pred.data_ptr(), _st()), "peer_merge_vote")
+
+    for r in range(G):
+        consume(r)            # the sessions' warm-up pass produced step 1
+    first = 0
+    for r in range(G):
+        sessions[r].run(qs.cuda(), check=False)
+        cnt = sessions[r].counters.tolist()
+        first += cnt[1]
+        assert cnt[5] == 0, cnt          # everything resolved by the in-graph completion
+    assert first > 0                     # ... and there WAS something to resolve
+    s_ref, i_ref = full.topk(qs, k, mode="exact", return_device=True)
+    for r in range(G):
+        consume(r)
+        torch.cuda.synchronize()
+        assert torch.equal(o_i, i_ref) and torch.equal(o_s, s_ref), r
+        assert torch.equal(pred, full.vote_from_idx(s_ref, i_ref))
+        assert peers.header(r)[:G].tolist() == [2] * G and peers.header(r)[16:16 + G].tolist() == [0] * G
+    peers.close()
+
+
 # ------------------------------------------------------------------------------------ full-size oracle checks
 def _oracle_subsample_check(gb, qs_dev, sims, idx, k, rows, chunk=64):
     """fp32 ``torch.mm`` + ``topk`` (qualitative_test.py:79-84) on the HOST copy of the unit bank for a
