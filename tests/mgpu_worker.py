@@ -85,6 +85,45 @@ def main():
     qd = base + 1e-4 * torch.randn(256, 256, generator=g)
     case(dup, torch.arange(nd) % 5, qd, 10, "near-duplicates", expect_uncertified=True)
 
+    # device-driven completion (on from k = 128): dense clusters make the first pass uncertified on every
+    # rank; the in-graph second pass resolves them BEFORE the peers are signalled, so no rank takes the host
+    # completion branch, nothing is redone, and the answers are still bit-identical
+    g = torch.Generator().manual_seed(17)
+    bases = torch.randn(8, 256, generator=g)
+    dense = (bases[:, None, :] + 1e-3 * torch.randn(8, 400, 256, generator=g)).reshape(-1, 256)
+    nb = 40000 + 3200
+    cbank = torch.cat([torch.randn(40000, 256, generator=g), dense])[torch.randperm(nb, generator=g)]
+    cl = torch.arange(nb) % 11
+    cq = bases.repeat_interleave(8, 0) + 1e-3 * torch.randn(64, 256, generator=g)
+    kd = 130
+    ref = hcir_b200.GalleryBank(cbank, cl, device=dev)
+    p_ref, s_ref, i_ref = ref.predict(cq, kd, return_neighbors=True)
+    assert ref.last_stats["uncertified"] > 0
+    sp = ShardPlan(nb, world)
+    gal = ShardedGallery(cbank[sp.start(rank):sp.stop(rank)], cl[sp.start(rank):sp.stop(rank)], n_total=nb, device=dev,
+                         classes=ref.classes_, exchange="peer")
+    qg = QueryShardedGallery(cbank, cl, device=dev, classes=ref.classes_, exchange="peer")
+    for rep in range(reps):
+        s, i = gal.topk(cq, kd)
+        assert torch.equal(i, i_ref) and torch.equal(s, s_ref), ("device completion", "gallery topk", rep)
+        assert gal.bank.last_stats["uncertified"] == 0, gal.bank.last_stats
+        assert torch.equal(gal.predict(cq, kd), p_ref) and torch.equal(qg.predict(cq, kd), p_ref)
+        assert qg.bank.last_stats["uncertified"] == 0, qg.bank.last_stats
+        s, i = qg.topk(cq, kd)
+        assert torch.equal(i, i_ref) and torch.equal(s, s_ref), ("device completion", "query topk", rep)
+    for obj in (gal, qg):
+        h = obj.submit_predict(cq.cuda(), kd)
+        assert torch.equal(h.result().cpu(), p_ref) and not h.redone
+    # (a gallery shard holds only 1/world of every dense cluster and may certify at once; a replica cannot)
+    first = qg.last_session.counters.tolist()[1]
+    tot = torch.tensor([first], device=dev)
+    dist.all_reduce(tot)
+    assert int(tot.item()) > 0, "the first pass should have left uncertified queries on the replicas"
+    gal.close()
+    qg.close()
+    del ref
+    checks += 1
+
     # more shapes than the session cache holds: evicted sessions close their peer regions collectively
     ref = hcir_b200.GalleryBank(bank, bl, device=dev)
     sp = ShardPlan(bank.shape[0], world)
