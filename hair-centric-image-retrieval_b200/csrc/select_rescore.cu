@@ -421,6 +421,9 @@ __device__ __forceinline__ void select_rescore_body(const K3Args& a, const int64
   // (measured, r2h: ranking the ~700 staged keys of the streaming regime directly -- one warp per key -- instead of
   //  cutting them down first doubles K3 there, 31 -> 62 us: n^2 / 32 warp steps is 11 us of issue slots)
   if (nstage > kc + 128) {
+    // wide CTAs (streaming regime) cut with 512 bins: warp 0 scans the bins alone while 31 warps wait at the
+    // barrier (14 % of the kernel's stall samples with 2048 bins), and ~700 staged keys need no finer cut
+    constexpr int kCutBins = kWide ? 512 : kBins;
     uint64_t* compact = reinterpret_cast<uint64_t*>(hist);  // the histogram's memory, reused after the scan
     constexpr int kCompactCap = kBins * 4 / 8;
     if (tid == 0) { scratch[15] = 0xFFFFFFFFu; scratch[16] = 0u; scratch[17] = 0u; }
@@ -439,20 +442,20 @@ __device__ __forceinline__ void select_rescore_body(const K3Args& a, const int64
       }
       if (lane == 0) { atomicMin(&scratch[15], mn); atomicMax(&scratch[16], mx); }
     }
-    for (int b = tid; b < kBins; b += kSelThreads) hist[b] = 0;
+    for (int b = tid; b < kCutBins; b += kSelThreads) hist[b] = 0;
     __syncthreads();
     const uint32_t lo = scratch[15], span = scratch[16] - lo;
     int shift = 0;
-    while ((span >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
+    while ((span >> shift) >= static_cast<uint32_t>(kCutBins)) ++shift;
     for (int i = tid; i < nstage; i += kSelThreads) {
-      HCIR_DEV_CHECK(((static_cast<uint32_t>(stage[i] >> 32) - lo) >> shift) < static_cast<uint32_t>(kBins));
+      HCIR_DEV_CHECK(((static_cast<uint32_t>(stage[i] >> 32) - lo) >> shift) < static_cast<uint32_t>(kCutBins));
       atomicAdd(&hist[(static_cast<uint32_t>(stage[i] >> 32) - lo) >> shift], 1u);
     }
     __syncthreads();
     if (warp == 0) {  // bin that holds the kc-th best, scanning from the top
-      constexpr int per = kBins / kWarp;
+      constexpr int per = kCutBins / kWarp;
       uint32_t sum = 0;
-      for (int j = 0; j < per; ++j) sum += hist[kBins - 1 - (per * lane + j)];
+      for (int j = 0; j < per; ++j) sum += hist[kCutBins - 1 - (per * lane + j)];
       uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < kWarp; o <<= 1) {
@@ -463,7 +466,7 @@ __device__ __forceinline__ void select_rescore_body(const K3Args& a, const int64
       if (excl < need && need <= incl) {
         uint32_t run = excl;
         for (int j = 0; j < per; ++j) {
-          const int b = kBins - 1 - (per * lane + j);
+          const int b = kCutBins - 1 - (per * lane + j);
           if (run + hist[b] >= need) {
             scratch[10] = static_cast<uint32_t>(b);
             scratch[11] = run + hist[b];  // keys at or above the cut
