@@ -739,6 +739,9 @@ class SearchSession:
             tail.out_lab = self.out_lab.data_ptr()
         if self.tail_hook is not None:
             self.tail_hook(self, tail)
+        if self.dev_completion and self._completion_plan() is None:
+            self.dev_completion = False           # (no sample-pass layout for the batch: cannot happen on
+            self.unc_cnt = self.unc_state[1:2]    #  the tensor path, but never leave the peers unsignalled)
         if self.dev_completion and tail.world > 0:
             tail.no_signal = 1   # the completion pass may still correct rows: IT signals the peers
         _lib.check(lib.hcir_select_rescore(self.q32.data_ptr(), b.g32.data_ptr(), b.ld, nq, b.n, k, b.idx_offset,
@@ -758,6 +761,18 @@ class SearchSession:
             self.post_out = self.post(self)
         self.kernels_per_run = kernels
 
+    def _completion_plan(self):
+        """Launch plan of the completion batch (RETRY_CAPACITY queries, up to 4x kc), or None."""
+        b = self.bank
+        kc = b.choose_kc(self.k)
+        plan2 = Plan()
+        for mult in (4, 3, 2, 1):   # widest kc whose plan still carries per-query thresholds
+            kc2 = max(kc, min(mult * kc, 2048))
+            _lib.check(b.lib.hcir_simtopk_plan(self.RETRY_CAPACITY, b.n, b.ld, kc2, b.sm_count, plan2), "simtopk_plan")
+            if plan2.sample_rows > 0:
+                return plan2
+        return None
+
     def _completion_pass(self, tail, st) -> int:
         """In-graph second pass over the queries K3 could not certify (GalleryBank._finish_uncertified has
         the reasoning): gather them into a compact batch with explicit thresholds (hcir_retry_setup), stream
@@ -766,17 +781,7 @@ class SearchSession:
         is STILL uncertified (near-duplicate galleries) for the exact kernel on the host's initiative."""
         b, lib, dev = self.bank, self.bank.lib, self.bank.device
         R, k = self.RETRY_CAPACITY, self.k
-        kc = b.choose_kc(k)
-        plan2 = Plan()
-        for mult in (4, 3, 2, 1):   # widest kc whose plan still carries per-query thresholds
-            kc2 = max(kc, min(mult * kc, 2048))
-            _lib.check(lib.hcir_simtopk_plan(R, b.n, b.ld, kc2, b.sm_count, plan2), "simtopk_plan")
-            if plan2.sample_rows > 0:
-                break
-        if plan2.sample_rows <= 0:   # (cannot happen on the tensor path: the gallery is big enough for a sample)
-            self.dev_completion = False
-            self.unc_cnt = self.unc_state[1:2]
-            return 0
+        plan2 = self._completion_plan()
         plan2.q_rows = R
         self.plan2 = plan2
         if getattr(self, "ws2", None) is None:
