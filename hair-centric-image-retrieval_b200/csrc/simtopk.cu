@@ -35,8 +35,11 @@ constexpr int kBBytes = kBlockN * kBlockK * 2;  // 32 KiB (per CTA: kBBytes / kC
 // 256 x 256 tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 query rows and HALF
 // of the gallery tile, which cuts the shared-memory traffic per flop by a third (the 1-CTA kernel
 // is bound by it) and leaves room for a 6-stage ring.
+#ifndef HCIR_MAIN_STAGES
+#define HCIR_MAIN_STAGES 4   // TMA ring depth of the 1-CTA kernel (A/B: 3 leaves 48 KiB of the SM for co-resident CTAs)
+#endif
 template <int kCtas> struct SimCfg {
-  static constexpr int kStages = (kCtas == 2) ? 6 : 4;
+  static constexpr int kStages = (kCtas == 2) ? 6 : HCIR_MAIN_STAGES;
   static constexpr int kBBytesCta = kBBytes / kCtas;
   static constexpr int kStageBytes = kABytes + kBBytesCta;
 };
