@@ -75,7 +75,7 @@ def parse():
     ap.add_argument("--pipeline", type=int, default=2,
                     help="steps in flight for the device-resident measurement (submit / result API); 1 = every "
                          "step waits for its own host-side check before the next is launched")
-    ap.add_argument("--pipeline-below-ms", type=float, default=1.0,
+    ap.add_argument("--pipeline-below-ms", type=float, default=2.0,
                     help="pipeline the submission only when the one-at-a-time step is shorter than this")
     ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
                     help="multi-GPU result exchange: the library's stores over NVLink peer memory or one NCCL all-gather "
