@@ -100,27 +100,29 @@ def main():
     p_ref, s_ref, i_ref = ref.predict(cq, kd, return_neighbors=True)
     assert ref.last_stats["uncertified"] > 0
     sp = ShardPlan(nb, world)
-    gal = ShardedGallery(cbank[sp.start(rank):sp.stop(rank)], cl[sp.start(rank):sp.stop(rank)], n_total=nb, device=dev,
-                         classes=ref.classes_, exchange="peer")
-    qg = QueryShardedGallery(cbank, cl, device=dev, classes=ref.classes_, exchange="peer")
-    for rep in range(reps):
-        s, i = gal.topk(cq, kd)
-        assert torch.equal(i, i_ref) and torch.equal(s, s_ref), ("device completion", "gallery topk", rep)
-        assert gal.bank.last_stats["uncertified"] == 0, gal.bank.last_stats
-        assert torch.equal(gal.predict(cq, kd), p_ref) and torch.equal(qg.predict(cq, kd), p_ref)
-        assert qg.bank.last_stats["uncertified"] == 0, qg.bank.last_stats
-        s, i = qg.topk(cq, kd)
-        assert torch.equal(i, i_ref) and torch.equal(s, s_ref), ("device completion", "query topk", rep)
-    for obj in (gal, qg):
-        h = obj.submit_predict(cq.cuda(), kd)
-        assert torch.equal(h.result().cpu(), p_ref) and not h.redone
-    # (a gallery shard holds only 1/world of every dense cluster and may certify at once; a replica cannot)
-    first = qg.last_session.counters.tolist()[1]
-    tot = torch.tensor([first], device=dev)
-    dist.all_reduce(tot)
-    assert int(tot.item()) > 0, "the first pass should have left uncertified queries on the replicas"
-    gal.close()
-    qg.close()
+    for exchange in ("peer", "nccl"):
+        gal = ShardedGallery(cbank[sp.start(rank):sp.stop(rank)], cl[sp.start(rank):sp.stop(rank)], n_total=nb,
+                             device=dev, classes=ref.classes_, exchange=exchange)
+        qg = QueryShardedGallery(cbank, cl, device=dev, classes=ref.classes_, exchange=exchange)
+        for rep in range(reps):
+            s, i = gal.topk(cq, kd)
+            assert torch.equal(i, i_ref) and torch.equal(s, s_ref), ("device completion", exchange, "gallery topk", rep)
+            assert gal.bank.last_stats["uncertified"] == 0, gal.bank.last_stats
+            assert torch.equal(gal.predict(cq, kd), p_ref) and torch.equal(qg.predict(cq, kd), p_ref)
+            assert qg.bank.last_stats["uncertified"] == 0, qg.bank.last_stats
+            s, i = qg.topk(cq, kd)
+            assert torch.equal(i, i_ref) and torch.equal(s, s_ref), ("device completion", exchange, "query topk", rep)
+        if exchange == "peer":
+            for obj in (gal, qg):
+                h = obj.submit_predict(cq.cuda(), kd)
+                assert torch.equal(h.result().cpu(), p_ref) and not h.redone
+        # (a gallery shard holds only 1/world of every dense cluster and may certify at once; a replica cannot)
+        first = qg.last_session.counters.tolist()[1]
+        tot = torch.tensor([first], device=dev)
+        dist.all_reduce(tot)
+        assert int(tot.item()) > 0, "the first pass should have left uncertified queries on the replicas"
+        gal.close()
+        qg.close()
     del ref
     checks += 1
 
