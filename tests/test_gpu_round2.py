@@ -386,6 +386,36 @@ def test_device_driven_completion_corrects_the_peer_rows_before_the_signal():
     peers.close()
 
 
+def test_unrepresentative_sample_cannot_break_exactness():
+    """The optimistic threshold assumes the strided sample is representative.  Here it is not: exactly
+    thr_rank of the SAMPLE rows (one per chunk) are near-copies of the query and nothing else is, so the
+    threshold lands on a planted row, fewer than k rows pass the filter, and the first pass cannot even fill
+    the top-k.  Exactness must not depend on the sample: the query is uncertified, completed, and equal to
+    the exact fp32 path -- through the eager path, the captured session and the in-graph completion."""
+    lib = _lib.load()
+    n, d, k, nq = 40000, 128, 20, 8
+    g = torch.Generator().manual_seed(29)
+    u = torch.nn.functional.normalize(torch.randn(1, d, generator=g), dim=1)
+    bank = torch.randn(n, d, generator=g)
+    plan = _lib.Plan()
+    _lib.check(lib.hcir_simtopk_plan(nq, n, lib.hcir_padded_dim(d), 2 * k + 64, 148, plan))
+    assert plan.sample_rows > 0 and plan.thr_rank < k          # the regime the test is about
+    for c in range(plan.thr_rank):                              # one planted row in each of thr_rank chunks
+        row = (c * plan.chunk_w + 3) * plan.sample_stride       # sample row i lives at gallery row i * stride
+        bank[row] = u[0] * 5.0 + 0.05 * torch.randn(d, generator=g)
+    qs = u + 1e-3 * torch.randn(nq, d, generator=g)
+    gb = GalleryBank(bank)
+    s_ex, i_ex = gb.topk(qs, k, mode="exact")
+    s1, i1 = gb.topk(qs, k, mode="tensor")
+    assert gb.last_stats["uncertified"] == nq, gb.last_stats   # nobody could be certified from the short lists
+    assert torch.equal(i1, i_ex) and torch.equal(s1, s_ex)
+    for dc in (False, True):
+        sess = SearchSession(gb, nq, k, vote=False, device_completion=dc)
+        _, s2, i2 = sess.run(qs.cuda())
+        assert gb.last_stats["uncertified_first_pass"] == nq
+        assert torch.equal(i2.cpu(), i_ex) and torch.equal(s2.cpu(), s_ex), dc
+
+
 # ------------------------------------------------------------------------------------ full-size oracle checks
 def _oracle_subsample_check(gb, qs_dev, sims, idx, k, rows, chunk=64):
     """fp32 ``torch.mm`` + ``topk`` (qualitative_test.py:79-84) on the HOST copy of the unit bank for a

@@ -66,3 +66,22 @@ def test_embeddings_npy_roundtrip(tmp_path):
     assert sorted(os.listdir(tmp_path)) == ["embeddings.npy", "image_paths.txt"]
     np.testing.assert_array_equal(np.load(tmp_path / "embeddings.npy"), emb)
     assert formats.load_paths(str(tmp_path)) == paths
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) runs on the host cores alone and prints ONE JSON
+    line with the contract's keys; the B200 arm's helpers import without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1",
+                        "--steps", "1", "--warmup", "0", "--cpu-sample", "64"], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
