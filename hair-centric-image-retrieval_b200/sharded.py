@@ -1,11 +1,15 @@
-"""Multi-GPU: the gallery is row-sharded over the ranks of one box (one process per GPU,
-``torch.distributed``; NCCL over NVLink on GPUs).  Each rank computes its exact local top-k,
-ONE all-gather of k candidates per query per rank follows, and a merge kernel (K5) produces
-the global top-k on every rank (no reference analogue -- the
-reference's kNN is single-process CPU, classification_engine.py:51,63).
+"""Multi-GPU: one process per GPU of one box (``torch.distributed`` for rendezvous; no
+reference analogue -- the reference's kNN is single-process CPU, classification_engine.py:51,63).
 
-``ShardPlan`` and ``exchange_candidates`` are backend-agnostic (tested with gloo on CPU);
-the local search and the merge are CUDA-only."""
+* ``ShardedGallery``: the gallery is row-sharded.  Each rank computes its exact local top-k; the tail of
+  K3 stores every query's k candidates straight into every rank's peer region over NVLink, and ONE more
+  kernel per rank waits for all blocks, merges them (K5) and votes -- or, with ``exchange="nccl"``, one
+  all-gather of the packed blocks + merge + vote.
+* ``QueryShardedGallery``: every rank holds the whole gallery and answers a slice of the query batch; the
+  predictions / top-k rows are exchanged the same way.
+
+``ShardPlan``, ``exchange_candidates`` and ``gather_rows`` are backend-agnostic (tested with gloo on CPU);
+the local search, the peer exchange and the merge are CUDA-only."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -23,8 +27,8 @@ import warnings
 from . import peer as _peer
 from .peer import PeerExchange
 
-# how the per-rank result blocks travel: "peer" = the library's own push over NVLink peer memory
-# (csrc/peer.cu, captured into the step's CUDA graph), "nccl" = one ncclAllGather
+# how the per-rank result blocks travel: "peer" = the library's own stores over NVLink peer memory
+# (K3's tail + csrc/peer.cu, captured into the step's CUDA graph), "nccl" = one ncclAllGather
 DEFAULT_EXCHANGE = os.environ.get("HCIR_EXCHANGE", "peer")
 
 
