@@ -416,6 +416,40 @@ def test_unrepresentative_sample_cannot_break_exactness():
         assert torch.equal(i2.cpu(), i_ex) and torch.equal(s2.cpu(), s_ex), dc
 
 
+def test_fuzz_tensor_path_equals_exact_path_bit_for_bit():
+    """Seeded random shapes and data shapes (clustered, heavy-tailed cluster sizes, duplicated rows, a few
+    zero rows): the tensor path (eager and captured, every K3 width the shape selects, host- and
+    device-driven completion) must return exactly what the fp32 CUDA-core path returns."""
+    rng = np.random.default_rng(2024)
+    for case in range(18):
+        d = int(rng.choice([64, 96, 256, 512, 768, 1024, 2048]))
+        n = int(rng.integers(9000, 120000 if d <= 768 else 40000))
+        nq = int(rng.choice([1, 7, 64, 129, 300, 700, 2500]))
+        k = int(rng.choice([1, 5, 20, 50, 100, 160, 300]))
+        if n < 8 * (2 * k + 64) or n < 4096:
+            continue
+        ncls = int(rng.integers(2, 40))
+        g = torch.Generator().manual_seed(1000 + case)
+        bank, _ = synth.make_clustered(n, d, ncls, 3000 + case)
+        if case % 3 == 0:      # a block of exact duplicates and two zero rows
+            bank[100:100 + min(k + 7, 200)] = bank[99]
+            bank[7] = 0.0
+            bank[n - 1] = 0.0
+        if case % 4 == 1:      # a tight cluster: many near-ties around the k-th neighbour
+            bank[2000:2000 + 3 * k + 50] = bank[1999] + 2e-3 * torch.randn(3 * k + 50, d, generator=g)
+        qs, _ = synth.make_clustered(nq, d, ncls, 4000 + case)
+        if case % 4 == 1:
+            qs[0] = bank[1999] * 0.7
+        gb = GalleryBank(bank)
+        s_ex, i_ex = gb.topk(qs, k, mode="exact")
+        s1, i1 = gb.topk(qs, k, mode="tensor")
+        assert torch.equal(i1, i_ex) and torch.equal(s1, s_ex), (case, n, d, nq, k, gb.last_stats)
+        sess = SearchSession(gb, nq, k, vote=False, device_completion=bool(case % 2))
+        _, s2, i2 = sess.run(qs.cuda())
+        assert torch.equal(i2.cpu(), i_ex) and torch.equal(s2.cpu(), s_ex), (case, n, d, nq, k, gb.last_stats)
+        del sess, gb
+
+
 # ------------------------------------------------------------------------------------ full-size oracle checks
 def _oracle_subsample_check(gb, qs_dev, sims, idx, k, rows, chunk=64):
     """fp32 ``torch.mm`` + ``topk`` (qualitative_test.py:79-84) on the HOST copy of the unit bank for a
