@@ -71,6 +71,19 @@ def _to_host(t: torch.Tensor, kind: str):
     return h.numpy() if kind == "numpy" else h
 
 
+def _to_host_many(ts, kind: str):
+    """Several device results -> the caller's flavour with ONE stream synchronisation."""
+    if kind == "torch_cuda":
+        return list(ts)
+    hs = []
+    for t in ts:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        hs.append(h)
+    torch.cuda.current_stream().synchronize()
+    return [h.numpy() if kind == "numpy" else h for h in hs]
+
+
 def l2_normalize(x: torch.Tensor, *, want_f32=True, want_bf16=True, want_delta=True, pad_rows_to: int = 1):
     """K1 on a device tensor [n, d] fp32 -> (unit fp32 [n, ld] | None, unit bf16 [n, ld] | None,
     delta [n] | None) with ld = d rounded up to 64 (zero padded).  ``F.normalize(x, dim=1)``
@@ -211,18 +224,20 @@ class GalleryBank:
         if not (1 <= k <= self.n):
             raise ValueError(f"k={k} must be in [1, N={self.n}]")
         with torch.cuda.device(self.device):
-            if not q.is_cuda:
-                q = q.contiguous().to(self.device, non_blocking=True)
-            elif q.device != self.device:
-                q = q.to(self.device)
             sess = self.session(q.shape[0], k, vote=False) if (use_graph and mode == "auto") else None
             if sess is not None:
-                _, sims, idx = sess.run(q)
+                # host queries go straight into the step's static input (one H2D copy, no staging tensor)
+                _, sims, idx = sess.run(q if q.is_cuda or q.is_pinned() else q.contiguous())
             else:
+                if not q.is_cuda:
+                    q = q.contiguous().to(self.device, non_blocking=True)
+                elif q.device != self.device:
+                    q = q.to(self.device)
                 sims, idx = self._topk_device(q, k, mode)
             if return_device or kind == "torch_cuda":
                 return sims, idx
-            return _to_host(sims, kind), _to_host(idx, kind)
+            sims_h, idx_h = _to_host_many([sims, idx], kind)
+            return sims_h, idx_h
 
     def _topk_device(self, q: torch.Tensor, k: int, mode: str = "auto"):
         sims, idx, _ = self._search(q, k, mode, None)

@@ -21,7 +21,7 @@ import torch.distributed as dist
 import os
 
 from . import _lib
-from .engine import GalleryBank, PendingStep, _as_2d_f32, _stream_ptr, _to_host
+from .engine import GalleryBank, PendingStep, _as_2d_f32, _stream_ptr, _to_host, _to_host_many
 import warnings
 
 from . import peer as _peer
@@ -287,7 +287,7 @@ class ShardedGallery:
                     return o_s, o_i, o_l
                 if kind == "torch_cuda":
                     return o_s, o_i
-                return _to_host(o_s, kind), _to_host(o_i, kind)
+                return tuple(_to_host_many([o_s, o_i], kind))
             sims, idx = self._local(q, int(k), mode)
             lab = self.bank.neighbour_labels(idx) if with_labels else None
             g_s, g_i, g_l = exchange_candidates(sims, idx, lab, self.group)
@@ -296,7 +296,7 @@ class ShardedGallery:
             return o_s, o_i, o_l
         if kind == "torch_cuda":
             return o_s, o_i
-        return _to_host(o_s, kind), _to_host(o_i, kind)
+        return tuple(_to_host_many([o_s, o_i], kind))
 
     def predict(self, queries, k: int, *, T=None, mode: str = "auto"):
         q, kind = _as_2d_f32(queries, "queries")
@@ -533,4 +533,4 @@ class QueryShardedGallery:
                 o_s, o_i = self._gather_rows(sims, sp), self._gather_rows(idx, sp)
         if kind == "torch_cuda":
             return o_s, o_i
-        return _to_host(o_s, kind), _to_host(o_i, kind)
+        return tuple(_to_host_many([o_s, o_i], kind))
