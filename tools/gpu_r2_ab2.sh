@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of K3 build options on the GPU box (rebuilds the library there): register budget and dot-product load grouping
+# A/B of K3 build options on the GPU box (rebuilds the library there through HCIR_NVCC_EXTRA): register budget
+# (-DHCIR_K3_THREADS_PER_SM) and dot-product load grouping (-DHCIR_DOT_GROUP); results: profiles/README.md r2d
 set -u
 mkdir -p gpurun_out
 T=${1:-r2d}
