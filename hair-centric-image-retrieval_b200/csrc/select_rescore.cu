@@ -852,7 +852,7 @@ static int launch_select(const float* q_f32, const float* g_f32, int ld, int64_t
   // CTA width: forced by the plan flags (measurement aid) or chosen from the shape
   const int width = (plan->flags & HCIR_FLAG_K3_WIDTH_MASK) >> HCIR_FLAG_K3_WIDTH_SHIFT;
   if (width == 3 || (width == 0 && nq <= 2 * static_cast<int64_t>(sms))) HCIR_LAUNCH_SEL(1024);
-  else if (width == 1 || (width == 0 && k <= 32 && nq >= 2048)) HCIR_LAUNCH_SEL(128);
+  else if (width == 1 || (width == 0 && k <= 32 && nq >= 512)) HCIR_LAUNCH_SEL(128);  // r3b sweep: 128 wins from ~600 queries
   else HCIR_LAUNCH_SEL(256);
 #undef HCIR_LAUNCH_SEL
   HCIR_CUDA_TRY(cudaGetLastError());
