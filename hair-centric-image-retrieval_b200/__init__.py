@@ -10,10 +10,11 @@ from .retrieval import (retrieve_similar_images, HairRetrievalB200, FlatIndex,  
                         compute_similarity_topk, clear_bank_cache)
 from .sharded import (ShardPlan, ShardedGallery, QueryShardedGallery, choose_sharding,  # noqa: F401
                       exchange_candidates)
+from .pipeline import HostPipeline, HostPending  # noqa: F401
 from . import synth, formats, metrics  # noqa: F401
 
 __all__ = [
     "GalleryBank", "FeatureBankBuilder", "PendingStep", "knn_topk", "knn_predict", "l2_normalize", "KNeighborsClassifierB200",
     "retrieve_similar_images", "HairRetrievalB200", "FlatIndex", "compute_similarity_topk",
-    "clear_bank_cache", "ShardPlan", "ShardedGallery", "QueryShardedGallery", "choose_sharding", "exchange_candidates", "synth", "formats", "metrics",
+    "clear_bank_cache", "ShardPlan", "ShardedGallery", "QueryShardedGallery", "choose_sharding", "exchange_candidates", "HostPipeline", "HostPending", "synth", "formats", "metrics",
 ]

@@ -603,6 +603,12 @@ class PendingStep:
         self._event, self._flags, self._needs_redo, self._results, self._redo = event, flags_host, needs_redo, results, redo
         self.redone = False
 
+    @property
+    def device_results(self):
+        """The results as enqueued (device tensors; final unless ``result()`` finds the batch must be
+        redone) -- for callers that queue further device work, e.g. the read-back on a copy stream."""
+        return self._results
+
     def result(self):
         if self._event is not None:
             self._event.synchronize()

@@ -65,6 +65,18 @@ def main():
                 for h in pend:
                     s, i = h.result()
                     assert torch.equal(i.cpu(), i_ref) and torch.equal(s.cpu(), s_ref), (tag, "submit_topk")
+                # host batches through the three-stream serving loop: host answers, on every rank
+                qh = qs.pin_memory()
+                for obj, want in ((qg, "topk"), (qg, "pred"), (gal, "pred")):
+                    pipe = hcir_b200.HostPipeline.for_gallery(obj, qs.shape[0], k, want=want)
+                    pend = [pipe.submit(qh) for _ in range(3)]
+                    for h in pend:
+                        r = h.result()
+                        if want == "topk":
+                            assert torch.equal(r[1], i_ref) and torch.equal(r[0], s_ref), (tag, "host pipeline topk")
+                        else:
+                            assert torch.equal(r, p_ref), (tag, "host pipeline pred", type(obj).__name__)
+                        assert h.redone == bool(expect_uncertified), (tag, "host pipeline redone")
                 pt_ref = ref.predict(qs, k, T=0.07)   # the temperature vote through both partitions
                 assert torch.equal(gal.predict(qs, k, T=0.07), pt_ref) and torch.equal(qg.predict(qs, k, T=0.07), pt_ref)
             checks += 1

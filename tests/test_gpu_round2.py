@@ -660,3 +660,49 @@ def test_kth_neighbour_euclidean_branch_and_metrics_on_device():
             aps[k].append(sp_ / min(len(gt_list), k) if gt_list else 0.0)
     for k in (10, 20, 50):
         assert abs(got["Recall"][k] - rec[k] / 40) < 1e-12 and abs(got["mAP"][k] - float(np.mean(aps[k]))) < 1e-12
+
+
+def test_host_pipeline_overlaps_copies_and_returns_the_synchronous_answers():
+    """HostPipeline: host batches in, host answers out, copies on their own streams.  Every batch must equal
+    the synchronous call on the same batch -- including a batch that the first pass cannot certify (the
+    unrepresentative-sample construction), which result() redoes -- for top-k and for both votes."""
+    from hcir_b200 import HostPipeline
+    lib = _lib.load()
+    n, d, k, nq, ncls = 40000, 128, 20, 8, 7
+    g = torch.Generator().manual_seed(31)
+    u = torch.nn.functional.normalize(torch.randn(1, d, generator=g), dim=1)
+    bank = torch.randn(n, d, generator=g)
+    plan = _lib.Plan()
+    _lib.check(lib.hcir_simtopk_plan(nq, n, lib.hcir_padded_dim(d), 2 * k + 64, 148, plan))
+    for c in range(plan.thr_rank):
+        bank[(c * plan.chunk_w + 3) * plan.sample_stride] = u[0] * 5.0 + 0.05 * torch.randn(d, generator=g)
+    labels = torch.randint(0, ncls, (n,), generator=g)
+    gb = GalleryBank(bank, labels.numpy(), classes=np.arange(ncls))
+    hard = (u + 1e-3 * torch.randn(nq, d, generator=g)).pin_memory()
+    batches = [torch.randn(nq, d, generator=g).pin_memory() for _ in range(5)]
+    batches.insert(2, hard)
+    want_topk = [gb.topk(b, k) for b in batches]
+    for depth in (1, 2, 3):
+        pipe = HostPipeline.for_bank(gb, nq, k, want="topk", depth=depth)
+        pend = [pipe.submit(b) for b in batches]          # more than `depth`: the oldest completes on its own
+        got = [p.result() for p in pend]
+        assert pend[2].redone and not pend[0].redone
+        for (s, i), (ws, wi) in zip(got, want_topk):
+            assert isinstance(s, torch.Tensor) and not s.is_cuda and s.is_pinned()
+            assert torch.equal(i, wi) and torch.equal(s, ws)
+        assert pend[1].result() is got[1]                 # idempotent
+    for T in (None, 0.07):
+        want_pred = [gb.predict(b, k, T=T) for b in batches]
+        pipe = HostPipeline.for_bank(gb, nq, k, want="pred", T=T, depth=2)
+        pend = []
+        for b in batches:
+            pend.append(pipe.submit(b.numpy()))           # numpy in -> numpy out
+        pipe.drain()
+        for p, w in zip(pend, want_pred):
+            r = p.result()
+            assert isinstance(r, np.ndarray) and r.dtype == np.int64
+            assert np.array_equal(r, np.asarray(w))
+    with pytest.raises(ValueError):
+        pipe.submit(torch.zeros(nq + 1, d))
+    with pytest.raises(ValueError):
+        HostPipeline.for_bank(GalleryBank(torch.randn(300, 16)), 4, 5)   # exact-path shape: nothing to pipeline
