@@ -25,9 +25,11 @@ the bank and answers a slice of the batch; HCIR_BENCH_SHARD / --shard = query) o
   * C2 (200k x 768, 10k queries, k=20 kNN vote: uniform = the reference's vote, and T=0.07).
 
 value   = queries/s with inputs resident in HBM (CUDA events, max over ranks)
-e2e     = queries/s through the reference-facing call (knn_topk / KNeighborsClassifierB200.predict /
-          the sharded gallery's topk / predict) on pinned HOST queries -> host results, H2D/D2H
-          copies inside the timed region (bank fitted once, as the reference builds its bank once)
+e2e     = queries/s from pinned HOST queries to host results, every batch's H2D and D2H copies inside
+          the timed region (bank fitted once, as the reference builds its bank once): `value` through
+          HostPipeline (two host batches in flight: copies on their own streams beside the searches),
+          `one_call_at_a_time` through the synchronous reference-facing call (knn_topk /
+          KNeighborsClassifierB200.predict / the sharded gallery's topk / predict)
 roofline= the dominant kernel (simtopk main pass) timed with CUDA events inside the timed steps:
           tensor bound: 2*Q*N_local*D flops / mean launch duration vs MEASURED_PEAKS.json bf16 burst
           peak; HBM bound (Q below the ridge): (N*D*2 + Q*D*2 + Q*k*12) bytes vs the copy bandwidth
