@@ -245,6 +245,28 @@ class ShardedGallery:
                                 "chunk_w": int(sess.plan.chunk_w)}
         return out
 
+    def _submit(self, queries, k: int, T, want: str) -> PendingStep:
+        q, kind = _as_2d_f32(queries, "queries")
+        self._check_k(k)
+        sync = (lambda: self.predict(q, k, T=T)) if want == "pred" else (lambda: self.topk(q, k))
+        ok = (self.exchange == "peer" and q.is_cuda and q.shape[0] > 0 and all(
+            GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world)))
+        if ok and (want == "topk" or self.bank.labels is not None):
+            with torch.cuda.device(self.device):
+                sess = self._packed_session(q.shape[0], int(k), want == "pred", T)
+                if sess is not None and (want == "topk" or sess.out_lab is not None):
+                    sess.run(q, check=False)
+                    self.last_session = sess
+                    out = sess.post_out
+                    xc = out["xchg"]
+                    xc.note_replay()
+                    slot, step = xc.header_async()
+                    res = out["pred"].clone() if want == "pred" else (out["sims"].clone(), out["idx"].clone())
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
+        return PendingStep(None, None, None, sync(), None)
+
     def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:
         """Pipelined ``predict`` for DEVICE queries (peer exchange only; anything else completes
         synchronously inside this call): the step is enqueued, the header of the peer region that
@@ -252,24 +274,11 @@ class ShardedGallery:
         [Q] int64 on the device decides -- identically on every rank -- whether the batch has to be
         redone through the synchronous path.  Up to two steps may be in flight (the peer regions are
         double-buffered)."""
-        q, kind = _as_2d_f32(queries, "queries")
-        ok = (self.exchange == "peer" and q.is_cuda and q.shape[0] > 0 and self.bank.labels is not None and all(
-            GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world)))
-        if ok:
-            with torch.cuda.device(self.device):
-                sess = self._packed_session(q.shape[0], int(k), True, T)
-                if sess is not None and sess.out_lab is not None:
-                    sess.run(q, check=False)
-                    self.last_session = sess
-                    xc = sess.post_out["xchg"]
-                    xc.note_replay()
-                    slot, step = xc.header_async()
-                    pred = sess.post_out["pred"].clone()
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), pred,
-                                       lambda: self.predict(q, k, T=T))
-        return PendingStep(None, None, None, self.predict(queries, k, T=T), None)
+        return self._submit(queries, k, T, "pred")
+
+    def submit_topk(self, queries, k: int) -> PendingStep:
+        """Pipelined ``topk`` for DEVICE queries: ``result()`` -> (sims, idx) [Q, k] on the device."""
+        return self._submit(queries, k, None, "topk")
 
     def topk(self, queries, k: int, *, mode: str = "auto", with_labels: bool = False):
         q, kind = _as_2d_f32(queries, "queries")

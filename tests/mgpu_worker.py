@@ -61,13 +61,14 @@ def main():
                     for h in pend:
                         assert torch.equal(h.result().cpu(), p_ref), (tag, "submit_predict", type(obj).__name__)
                         assert h.redone == bool(expect_uncertified), (tag, "redone", type(obj).__name__)
-                pend = [qg.submit_topk(qc, k), qg.submit_topk(qc, k)]
-                for h in pend:
-                    s, i = h.result()
-                    assert torch.equal(i.cpu(), i_ref) and torch.equal(s.cpu(), s_ref), (tag, "submit_topk")
+                for obj in (gal, qg):
+                    pend = [obj.submit_topk(qc, k), obj.submit_topk(qc, k)]
+                    for h in pend:
+                        s, i = h.result()
+                        assert torch.equal(i.cpu(), i_ref) and torch.equal(s.cpu(), s_ref), (tag, "submit_topk", type(obj).__name__)
                 # host batches through the three-stream serving loop: host answers, on every rank
                 qh = qs.pin_memory()
-                for obj, want in ((qg, "topk"), (qg, "pred"), (gal, "pred")):
+                for obj, want in ((qg, "topk"), (qg, "pred"), (gal, "pred"), (gal, "topk")):
                     pipe = hcir_b200.HostPipeline.for_gallery(obj, qs.shape[0], k, want=want)
                     pend = [pipe.submit(qh) for _ in range(3)]
                     for h in pend:
