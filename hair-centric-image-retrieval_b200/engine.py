@@ -604,6 +604,12 @@ class PendingStep:
         self.redone = False
 
     @property
+    def ready_event(self):
+        """The CUDA event recorded behind the step's results on the stream that produced them (None once
+        ``result()`` has run, or for a step that completed synchronously)."""
+        return self._event
+
+    @property
     def device_results(self):
         """The results as enqueued (device tensors; final unless ``result()`` finds the batch must be
         redone) -- for callers that queue further device work, e.g. the read-back on a copy stream."""
@@ -964,7 +970,7 @@ def _bank_session(self, nq: int, k: int, *, T=None, vote: bool = True, profile: 
     cache = self.__dict__.setdefault("_sessions_collective" if post is not None else "_sessions", {})
     s = cache.get(key)
     if s is None:
-        if len(cache) >= 4:  # each session owns a workspace: keep a handful
+        if len(cache) >= 8:  # each session owns a workspace: keep a handful
             old = cache.pop(next(iter(cache)))
             xc = getattr(old, "xchg", None)
             if xc is not None:   # every rank evicts the same session at the same call -> collective close

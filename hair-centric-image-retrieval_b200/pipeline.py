@@ -129,8 +129,10 @@ class HostPipeline:
             main.wait_event(ev_in)
             pend = self._submit_device(stage)
             dev = _flatten(self._pick(pend.device_results))
-            ev_main = torch.cuda.Event()
-            ev_main.record()
+            ev_main = pend.ready_event      # recorded on the stream that produced the results (a lane stream, maybe)
+            if ev_main is None:
+                ev_main = torch.cuda.Event()
+                ev_main.record()
             host = []
             with torch.cuda.stream(self._s_out):
                 self._s_out.wait_event(ev_main)

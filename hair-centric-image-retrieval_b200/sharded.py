@@ -132,6 +132,26 @@ class ShardedGallery:
         self.exchange = _resolve_exchange(exchange, group, self.device)
         self.profile = False       # bench.py: capture per-kernel events inside the graph
         self.last_session = None
+        # Pipelined submissions (submit_*) rotate over `lanes` CUDA streams, each with its own captured
+        # session and peer channel, so the latency-bound tail of step i (K3, wait + merge + vote) runs
+        # beside the sample pass / gallery stream of step i+1.  None = 2 lanes in the streaming regime
+        # (one query tile, where that tail is a fifth of the step), 1 otherwise (measured: no gain when
+        # the step is paced by the power-capped tensor pass).  HCIR_LANES overrides.
+        self.lanes = int(os.environ["HCIR_LANES"]) if os.environ.get("HCIR_LANES") else None
+        self._lane_streams = {}
+        self._submitted = 0
+
+    def _lane(self, nq: int):
+        """-> (lane index, stream | None) for the next pipelined submission (the same on every rank)."""
+        lanes = self.lanes if self.lanes else (2 if nq <= 128 else 1)
+        lane = self._submitted % max(1, lanes)
+        self._submitted += 1
+        if lane == 0:
+            return 0, None          # lane 0 is the caller's stream
+        st = self._lane_streams.get(lane)
+        if st is None:
+            st = self._lane_streams[lane] = torch.cuda.Stream(device=self.device)
+        return lane, st
 
     def _local(self, q: torch.Tensor, k: int, mode: str):
         """Exact local top-min(k, n_local), padded to width k with (-inf, -1)."""
@@ -202,8 +222,8 @@ class ShardedGallery:
             pred = self.bank.vote_from_labels(o_s, o_l, T=T)
         return {"gathered": gathered, "sims": o_s, "idx": o_i, "lab": o_l, "pred": pred}
 
-    def _packed_session(self, nq: int, k: int, want_vote: bool, T):
-        key = ("gallery-sharded", self.world, self.exchange, want_vote, None if T is None else float(T))
+    def _packed_session(self, nq: int, k: int, want_vote: bool, T, lane: int = 0):
+        key = ("gallery-sharded", self.world, self.exchange, want_vote, None if T is None else float(T), lane)
         if self.exchange == "peer":
             return self.bank.session(nq, k, vote=False, profile=self.profile, pack=True, tail_hook=self._tail_peer,
                                      post=lambda s_: self._post_peer(s_, want_vote, T), post_key=key)
@@ -253,18 +273,23 @@ class ShardedGallery:
             GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world)))
         if ok and (want == "topk" or self.bank.labels is not None):
             with torch.cuda.device(self.device):
-                sess = self._packed_session(q.shape[0], int(k), want == "pred", T)
-                if sess is not None and (want == "topk" or sess.out_lab is not None):
-                    sess.run(q, check=False)
-                    self.last_session = sess
-                    out = sess.post_out
-                    xc = out["xchg"]
-                    xc.note_replay()
-                    slot, step = xc.header_async()
-                    res = out["pred"].clone() if want == "pred" else (out["sims"].clone(), out["idx"].clone())
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
+                lane, st = self._lane(q.shape[0])
+                cur = torch.cuda.current_stream()
+                if st is not None:
+                    st.wait_stream(cur)      # the queries were produced on the caller's stream
+                with torch.cuda.stream(st if st is not None else cur):
+                    sess = self._packed_session(q.shape[0], int(k), want == "pred", T, lane)
+                    if sess is not None and (want == "topk" or sess.out_lab is not None):
+                        sess.run(q, check=False)
+                        self.last_session = sess
+                        out = sess.post_out
+                        xc = out["xchg"]
+                        xc.note_replay()
+                        slot, step = xc.header_async()
+                        res = out["pred"].clone() if want == "pred" else (out["sims"].clone(), out["idx"].clone())
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
         return PendingStep(None, None, None, sync(), None)
 
     def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:

@@ -57,12 +57,12 @@ def main():
             if exchange == "peer":   # pipelined submission: two steps in flight, checks read one step late
                 qc = qs.cuda()
                 for obj in (gal, qg):
-                    pend = [obj.submit_predict(qc, k), obj.submit_predict(qc, k)]
+                    pend = [obj.submit_predict(qc, k) for _ in range(3)]
                     for h in pend:
                         assert torch.equal(h.result().cpu(), p_ref), (tag, "submit_predict", type(obj).__name__)
                         assert h.redone == bool(expect_uncertified), (tag, "redone", type(obj).__name__)
                 for obj in (gal, qg):
-                    pend = [obj.submit_topk(qc, k), obj.submit_topk(qc, k)]
+                    pend = [obj.submit_topk(qc, k) for _ in range(3)]
                     for h in pend:
                         s, i = h.result()
                         assert torch.equal(i.cpu(), i_ref) and torch.equal(s.cpu(), s_ref), (tag, "submit_topk", type(obj).__name__)
@@ -88,6 +88,9 @@ def main():
     bank, bl = synth.make_clustered(40000, 256, 13, 91)
     qs, _ = synth.make_clustered(1001, 256, 13, 92)          # ragged: 1001 queries over `world` ranks
     case(bank, bl, qs, 20, "clustered")
+    # one query tile: pipelined submissions over gallery shards alternate between two lanes (streams), each
+    # with its own captured session and peer channel
+    case(bank, bl, qs[:64], 20, "streaming regime (two lanes)")
     if world <= 4:
         case(bank[:30011], bl[:30011], qs[:257], 7, "ragged gallery")
     # near-duplicate gallery: every query is uncertified -> the collective completion branch

@@ -1,6 +1,6 @@
 """Experiment: two SearchSessions of the same shape on two CUDA streams, submitted alternately, so that the
 tail of step i (K3: DRAM/latency-bound) overlaps the main pass of step i+1 (tensor-bound).
-    python tools/exp_lanes.py C3|C2 [steps]
+    python tools/exp_lanes.py C3|C2|C4 [steps] [gallery rows] [lanes]
 Prints ms/step for one lane (the bench's `value` path) and for two lanes."""
 import os
 import sys
@@ -19,6 +19,9 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C3"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     cfg = dict(synth.CONFIGS[name])
+    if len(sys.argv) > 3:
+        cfg["n"] = int(sys.argv[3])      # e.g. C4 60 1250000: one rank's share of the 10M gallery at 8 GPUs
+    nlanes = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     bank, bl = synth.make_clustered(cfg["n"], cfg["d"], cfg["classes"], 1234, device=dev)
@@ -26,8 +29,8 @@ def main():
     vote = name != "C3"
     gb = hcir_b200.GalleryBank(bank, bl if vote else None, device=dev)
     del bank
-    lanes = [SearchSession(gb, cfg["q"], cfg["k"], vote=vote) for _ in range(2)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    lanes = [SearchSession(gb, cfg["q"], cfg["k"], vote=vote) for _ in range(nlanes)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nlanes)]
     for s in lanes:
         s.input.copy_(qs)
     torch.cuda.synchronize()
@@ -49,7 +52,7 @@ def main():
         torch.cuda.synchronize()
         return t0.elapsed_time(t1) / count
 
-    for nl in (1, 2, 1, 2):
+    for nl in (1, nlanes, 1, nlanes, 2):
         run(nl, 5)
         ms = run(nl, steps)
         print(f"{name} lanes={nl}: {ms:.4f} ms/step  {cfg['q'] / ms * 1e3:,.0f} q/s", flush=True)
