@@ -107,7 +107,35 @@ def merge_topk(g_sims: torch.Tensor, g_idx: torch.Tensor, g_lab: torch.Tensor | 
     return out_sim, out_idx, out_lab
 
 
-class ShardedGallery:
+class _Lanes:
+    """Pipelined submissions (``submit_*``) rotate over ``lanes`` CUDA streams, each with its own captured
+    session and peer channel, so the latency-bound tail of step i (K3, wait + merge + vote) runs beside
+    the sample pass / main pass of step i+1 instead of in front of it.  ``lanes = None``: 3 lanes when a
+    rank's step is short (its query rows x its gallery rows <= 1.1e9 scores, i.e. <= ~1.5 ms), 1 otherwise
+    (one GPU, C3 / C2 at full batch: no gain, the step is paced by the power-capped tensor pass).  Measured
+    with two steps in flight on 2 GPUs: 1.25M x 768 shard, 64 queries: 0.361 -> 0.326 (2 lanes) -> 0.314 ms
+    (3) -> 0.303 (4 lanes, 4 in flight); replicas, 512 queries/rank on 1M x 768: 0.819 -> 0.756; 1250
+    queries/rank on 200k x 768: 0.436 -> 0.370; 5000/rank: 1.479 -> 1.405.  HCIR_LANES overrides."""
+
+    def _init_lanes(self):
+        self.lanes = int(os.environ["HCIR_LANES"]) if os.environ.get("HCIR_LANES") else None
+        self._lane_streams = {}
+        self._submitted = 0
+
+    def _lane(self, nq_per_rank: int, n_local: int):
+        """-> (lane index, stream | None) for the next pipelined submission (the same on every rank)."""
+        lanes = self.lanes if self.lanes else (3 if nq_per_rank * n_local <= 1.1e9 else 1)
+        lane = self._submitted % max(1, lanes)
+        self._submitted += 1
+        if lane == 0:
+            return 0, None          # lane 0 is the caller's stream
+        st = self._lane_streams.get(lane)
+        if st is None:
+            st = self._lane_streams[lane] = torch.cuda.Stream(device=self.device)
+        return lane, st
+
+
+class ShardedGallery(_Lanes):
     """Rank-local shard of a global gallery + the exchange/merge step.
 
     ``features_local`` are THIS rank's rows [plan.start(rank), plan.stop(rank)); queries are
@@ -132,26 +160,7 @@ class ShardedGallery:
         self.exchange = _resolve_exchange(exchange, group, self.device)
         self.profile = False       # bench.py: capture per-kernel events inside the graph
         self.last_session = None
-        # Pipelined submissions (submit_*) rotate over `lanes` CUDA streams, each with its own captured
-        # session and peer channel, so the latency-bound tail of step i (K3, wait + merge + vote) runs
-        # beside the sample pass / gallery stream of step i+1.  None = 2 lanes in the streaming regime
-        # (one query tile, where that tail is a fifth of the step), 1 otherwise (measured: no gain when
-        # the step is paced by the power-capped tensor pass).  HCIR_LANES overrides.
-        self.lanes = int(os.environ["HCIR_LANES"]) if os.environ.get("HCIR_LANES") else None
-        self._lane_streams = {}
-        self._submitted = 0
-
-    def _lane(self, nq: int):
-        """-> (lane index, stream | None) for the next pipelined submission (the same on every rank)."""
-        lanes = self.lanes if self.lanes else (2 if nq <= 128 else 1)
-        lane = self._submitted % max(1, lanes)
-        self._submitted += 1
-        if lane == 0:
-            return 0, None          # lane 0 is the caller's stream
-        st = self._lane_streams.get(lane)
-        if st is None:
-            st = self._lane_streams[lane] = torch.cuda.Stream(device=self.device)
-        return lane, st
+        self._init_lanes()
 
     def _local(self, q: torch.Tensor, k: int, mode: str):
         """Exact local top-min(k, n_local), padded to width k with (-inf, -1)."""
@@ -273,7 +282,7 @@ class ShardedGallery:
             GalleryBank.tensor_path_for(self.plan.size(r), int(k)) for r in range(self.world)))
         if ok and (want == "topk" or self.bank.labels is not None):
             with torch.cuda.device(self.device):
-                lane, st = self._lane(q.shape[0])
+                lane, st = self._lane(q.shape[0], self.plan.size(0))
                 cur = torch.cuda.current_stream()
                 if st is not None:
                     st.wait_stream(cur)      # the queries were produced on the caller's stream
@@ -378,7 +387,7 @@ def gather_rows(local: torch.Tensor, sp: ShardPlan, group=None) -> torch.Tensor:
     return torch.cat([out[r * hmax: r * hmax + sp.size(r)] for r in range(world)], 0)
 
 
-class QueryShardedGallery:
+class QueryShardedGallery(_Lanes):
     """Every rank holds the whole gallery; rank r answers the contiguous query slice
     [ShardPlan(Q, world).start(r), stop(r)) and every rank receives everybody's answers.  Results are
     bit-identical to the single-GPU result by construction (each query is answered by exactly the
@@ -397,6 +406,7 @@ class QueryShardedGallery:
         self.exchange = _resolve_exchange(exchange, group, self.device)
         self.profile = False       # bench.py: capture per-kernel events inside the graph
         self.last_session = None
+        self._init_lanes()
 
     def _slice(self, q: torch.Tensor):
         sp = ShardPlan(int(q.shape[0]), self.world)
@@ -423,7 +433,7 @@ class QueryShardedGallery:
         """COLLECTIVE: drop the cached sessions and close their peer channels (IPC mappings, regions)."""
         self.bank.drop_sessions()
 
-    def _issue_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T, want: str = "pred"):
+    def _issue_peer(self, mine: torch.Tensor, sp: ShardPlan, k: int, T, want: str = "pred", lane: int = 0):
         """Enqueue the whole step (one graph launch per rank incl. the result exchange); None if the
         tensor path does not apply.  -> (session, exchange, sizes, hmax)
 
@@ -444,11 +454,11 @@ class QueryShardedGallery:
         if want == "pred":
             sess = self.bank.session(hmax, k, T=T, profile=self.profile,
                                      tail_hook=lambda s_, t_: self._tail_peer(s_, t_, _lib.PAYLOAD_PRED, hmax * 8),
-                                     post=self._post_peer, post_key=("query-sharded", self.world, hmax))
+                                     post=self._post_peer, post_key=("query-sharded", self.world, hmax, lane))
         else:
             sess = self.bank.session(hmax, k, vote=False, pack=True, profile=self.profile,
                                      tail_hook=lambda s_, t_: self._tail_peer(s_, t_, _lib.PAYLOAD_BLOCK, s_.block_bytes),
-                                     post=self._post_peer, post_key=("query-sharded-topk", self.world, hmax))
+                                     post=self._post_peer, post_key=("query-sharded-topk", self.world, hmax, lane))
         if sess is None:
             return None
         sess.run(mine, check=False)
@@ -486,15 +496,20 @@ class QueryShardedGallery:
         if self.exchange == "peer" and q.is_cuda:
             sp, mine = self._slice(q)
             with torch.cuda.device(self.device):
-                issued = self._issue_peer(mine, sp, int(k), T, want)
-                if issued is not None:
-                    sess, xc, sizes, hmax = issued
-                    slot, step = xc.header_async()
-                    res = self._gathered_preds(xc, sizes, hmax) if want == "pred" else \
-                        self._gathered_topk(xc, sizes, hmax, int(k))
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
+                lane, st = self._lane(sp.size(0), self.bank.n)
+                cur = torch.cuda.current_stream()
+                if st is not None:
+                    st.wait_stream(cur)      # the queries were produced on the caller's stream
+                with torch.cuda.stream(st if st is not None else cur):
+                    issued = self._issue_peer(mine, sp, int(k), T, want, lane)
+                    if issued is not None:
+                        sess, xc, sizes, hmax = issued
+                        slot, step = xc.header_async()
+                        res = self._gathered_preds(xc, sizes, hmax) if want == "pred" else \
+                            self._gathered_topk(xc, sizes, hmax, int(k))
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
         return PendingStep(None, None, None, sync(), None)
 
     def submit_predict(self, queries, k: int, *, T=None) -> PendingStep:
