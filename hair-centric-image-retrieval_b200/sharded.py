@@ -111,11 +111,16 @@ class _Lanes:
     """Pipelined submissions (``submit_*``) rotate over ``lanes`` CUDA streams, each with its own captured
     session and peer channel, so the latency-bound tail of step i (K3, wait + merge + vote) runs beside
     the sample pass / main pass of step i+1 instead of in front of it.  ``lanes = None``: 3 lanes when a
-    rank's step is short (its query rows x its gallery rows <= 1.1e9 scores, i.e. <= ~1.5 ms), 1 otherwise
-    (one GPU, C3 / C2 at full batch: no gain, the step is paced by the power-capped tensor pass).  Measured
-    with two steps in flight on 2 GPUs: 1.25M x 768 shard, 64 queries: 0.361 -> 0.326 (2 lanes) -> 0.314 ms
-    (3) -> 0.303 (4 lanes, 4 in flight); replicas, 512 queries/rank on 1M x 768: 0.819 -> 0.756; 1250
-    queries/rank on 200k x 768: 0.436 -> 0.370; 5000/rank: 1.479 -> 1.405.  HCIR_LANES overrides."""
+    rank's step is short -- its query rows x its gallery rows <= ``LANE_MAX_SCORES`` -- and 1 otherwise.
+    Measured, two steps in flight (profiles/README.md): 8 GPUs, 10M x 768 gallery in shards, 64 queries:
+    0.361 -> 0.322 ms (2 GPUs, same shard shape: 0.361 -> 0.326 with 2 lanes -> 0.314 with 3 -> 0.303 with 4
+    lanes and 4 in flight); 8 GPUs, 1M x 768 in shards, 4096 queries: 1.217 -> 1.138 ms; 8 GPUs, 200k x 768
+    replicas, 1250 queries per rank: 0.412 -> 0.377 ms.  NOT where the tensor pass dominates the step: 1M x
+    768 replicas at 512 queries per rank gained on 2 GPUs (0.819 -> 0.756 ms) but lost on 8 (0.753 -> 0.787:
+    a rank whose next main pass starts first delays its own K3, and seven peers wait for it), and one GPU
+    at full batch shows nothing (the step is paced by the power-capped tensor pass).  HCIR_LANES overrides."""
+
+    LANE_MAX_SCORES = 3.0e8
 
     def _init_lanes(self):
         self.lanes = int(os.environ["HCIR_LANES"]) if os.environ.get("HCIR_LANES") else None
@@ -124,7 +129,7 @@ class _Lanes:
 
     def _lane(self, nq_per_rank: int, n_local: int):
         """-> (lane index, stream | None) for the next pipelined submission (the same on every rank)."""
-        lanes = self.lanes if self.lanes else (3 if nq_per_rank * n_local <= 1.1e9 else 1)
+        lanes = self.lanes if self.lanes else (3 if nq_per_rank * n_local <= self.LANE_MAX_SCORES else 1)
         lane = self._submitted % max(1, lanes)
         self._submitted += 1
         if lane == 0:
@@ -142,6 +147,8 @@ class ShardedGallery(_Lanes):
     replicated on every rank.  Results are identical on every rank and bit-identical to the
     single-GPU result (local lists are exact fp32 canonical lists, the merge is a pure
     sort-merge on (sim desc, idx asc))."""
+
+    LANE_MAX_SCORES = 6.0e8   # every rank re-scores ALL queries: the tail stays long next to the shard's main pass
 
     def __init__(self, features_local, labels_local=None, *, n_total: int, group=None, device=None,
                  classes=None, exchange: str | None = None):
