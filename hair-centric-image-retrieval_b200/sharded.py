@@ -107,6 +107,16 @@ def merge_topk(g_sims: torch.Tensor, g_idx: torch.Tensor, g_lab: torch.Tensor | 
     return out_sim, out_idx, out_lab
 
 
+def _hand_over(res, lane_stream, caller_stream):
+    """Results allocated on a lane stream are consumed on the caller's stream: tell the caching allocator,
+    so that a block the caller drops is not handed to the lane's next step while the caller's kernels
+    still read it."""
+    if lane_stream is None:
+        return
+    for t in ((res,) if isinstance(res, torch.Tensor) else res):
+        t.record_stream(caller_stream)
+
+
 class _Lanes:
     """Pipelined submissions (``submit_*``) rotate over ``lanes`` CUDA streams, each with its own captured
     session and peer channel, so the latency-bound tail of step i (K3, wait + merge + vote) runs beside
@@ -303,6 +313,7 @@ class ShardedGallery(_Lanes):
                         xc.note_replay()
                         slot, step = xc.header_async()
                         res = out["pred"].clone() if want == "pred" else (out["sims"].clone(), out["idx"].clone())
+                        _hand_over(res, st, cur)
                         ev = torch.cuda.Event()
                         ev.record()
                         return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
@@ -514,6 +525,7 @@ class QueryShardedGallery(_Lanes):
                         slot, step = xc.header_async()
                         res = self._gathered_preds(xc, sizes, hmax) if want == "pred" else \
                             self._gathered_topk(xc, sizes, hmax, int(k))
+                        _hand_over(res, st, cur)
                         ev = torch.cuda.Event()
                         ev.record()
                         return PendingStep(ev, slot, lambda f: any(c > 0 for c in xc.metas_of(f, step)), res, sync)
