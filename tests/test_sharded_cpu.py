@@ -120,3 +120,30 @@ def test_choose_sharding_policy():
     assert choose_sharding(10_000_000, 64, 8) == "gallery"       # C4: streaming regime
     assert choose_sharding(10_000_000, 16_384, 8, d=2048) == "gallery"  # C5: replica would not fit the budget
     assert choose_sharding(200_000, 1000, 8) == "gallery"        # too few query tiles per rank
+
+
+def test_lane_rotation_rule(monkeypatch):
+    """Pipelined submissions rotate over three lanes only where a rank's step is short (sharded._Lanes):
+    the same decision and the same lane order on every rank, lane 0 = the caller's stream."""
+    import torch
+    from hcir_b200.sharded import QueryShardedGallery, ShardedGallery, _Lanes
+
+    monkeypatch.delenv("HCIR_LANES", raising=False)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: object())
+
+    def lanes_of(cls, nq, n_local, count=6):
+        obj = cls.__new__(cls)
+        obj.device = "cpu"
+        obj._init_lanes()
+        out = [obj._lane(nq, n_local) for _ in range(count)]
+        assert all((st is None) == (lane == 0) for lane, st in out)
+        return [lane for lane, _ in out]
+
+    assert lanes_of(ShardedGallery, 64, 1_250_000) == [0, 1, 2, 0, 1, 2]         # C4 shard at 8 GPUs
+    assert lanes_of(ShardedGallery, 4096, 125_000) == [0, 1, 2, 0, 1, 2]         # C3 in gallery shards at 8 GPUs
+    assert lanes_of(ShardedGallery, 4096, 500_000) == [0] * 6                    # ... at 2 GPUs: long step
+    assert lanes_of(QueryShardedGallery, 1250, 200_000) == [0, 1, 2, 0, 1, 2]    # C2 replicas at 8 GPUs
+    assert lanes_of(QueryShardedGallery, 512, 1_000_000) == [0] * 6              # C3 replicas at 8 GPUs (measured: worse)
+    monkeypatch.setenv("HCIR_LANES", "2")
+    assert lanes_of(QueryShardedGallery, 512, 1_000_000, 4) == [0, 1, 0, 1]
+    assert issubclass(ShardedGallery, _Lanes) and issubclass(QueryShardedGallery, _Lanes)
